@@ -1,0 +1,48 @@
+import glob
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    meta = json.loads(str(z["meta"]))
+    return meta, {k: z[k] for k in z.files if k != "meta"}
+
+
+def golden_fft_cases():
+    names = []
+    for p in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))):
+        n = os.path.basename(p)[:-4]
+        if n.startswith(("lowcut", "highcut", "eq3fft")):
+            names.append(n)
+    return names
+
+
+def rms(a):
+    a = np.asarray(a, dtype=np.float64)
+    return float(np.sqrt(np.mean(a * a))) if a.size else 0.0
+
+
+@pytest.fixture(scope="session")
+def gpu_lib():
+    """The ctypes-loaded C-ABI library on a machine with a GPU (fails loudly otherwise)."""
+    from pyaudiodsptools_b200 import _native
+    lib = _native.load()
+    n = _native.device_count()
+    if n < 1:
+        pytest.fail("gpu-marked test running without a CUDA device")
+    return lib
