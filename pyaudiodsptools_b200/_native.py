@@ -1,0 +1,227 @@
+"""ctypes binding of libadt_b200.so (include/adt_b200.h).
+
+No PyTorch, no cupy: device memory, streams and events all go through the C
+ABI.  Importing this module never needs a GPU; *using* it does, and fails
+loudly (AdtError) when there is none — there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libadt_b200.so")
+NCCL_UNIQUE_ID_BYTES = 128
+
+
+class AdtError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"adt_b200 error {status}: {message}")
+        self.status = status
+
+
+class FirDesc(C.Structure):
+    _fields_ = [("fft_size", C.c_int32), ("hop", C.c_int32), ("n0", C.c_int32), ("back", C.c_int32),
+                ("mask_is_real", C.c_int32), ("chunk", C.c_int32), ("n_channels", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+_P = C.c_void_p
+_F = C.POINTER(C.c_float)
+# name -> (restype, argtypes); every symbol include/adt_b200.h declares
+PROTOTYPES = {
+    "adt_version": (C.c_char_p, []),
+    "adt_status_string": (C.c_char_p, [C.c_int]),
+    "adt_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "adt_ctx_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "adt_ctx_destroy": (C.c_int, [_P]),
+    "adt_last_error": (C.c_char_p, [_P]),
+    "adt_ctx_sync": (C.c_int, [_P]),
+    "adt_ctx_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "adt_ctx_device_name": (C.c_int, [_P, C.c_char_p, C.c_size_t]),
+    "adt_malloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
+    "adt_free": (C.c_int, [_P, _P]),
+    "adt_malloc_host": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
+    "adt_free_host": (C.c_int, [_P, _P]),
+    "adt_memset": (C.c_int, [_P, _P, C.c_int, C.c_size_t]),
+    "adt_memcpy_h2d": (C.c_int, [_P, _P, _P, C.c_size_t]),
+    "adt_memcpy_d2h": (C.c_int, [_P, _P, _P, C.c_size_t]),
+    "adt_memcpy_d2d": (C.c_int, [_P, _P, _P, C.c_size_t]),
+    "adt_event_create": (C.c_int, [_P, C.POINTER(_P)]),
+    "adt_event_destroy": (C.c_int, [_P]),
+    "adt_event_record": (C.c_int, [_P]),
+    "adt_event_elapsed_ms": (C.c_int, [_P, _P, C.POINTER(C.c_float)]),
+    "adt_fir_create": (C.c_int, [_P, C.POINTER(FirDesc), _P, C.POINTER(_P)]),
+    "adt_fir_destroy": (C.c_int, [_P]),
+    "adt_fir_process_dev": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int32]),
+    "adt_fir_process_host": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int32]),
+    "adt_fir_apply_host": (C.c_int, [_P, _P, _P]),
+    "adt_fir_apply_dev": (C.c_int, [_P, _P, _P]),
+    "adt_fir_reset": (C.c_int, [_P]),
+    "adt_biquad_create": (C.c_int, [_P, C.POINTER(C.c_double), C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "adt_biquad_destroy": (C.c_int, [_P]),
+    "adt_biquad_reset": (C.c_int, [_P]),
+    "adt_biquad_apply_dev": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64]),
+    "adt_biquad_apply_host": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64]),
+    "adt_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "adt_comm_create": (C.c_int, [_P, C.c_char_p, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "adt_comm_destroy": (C.c_int, [_P]),
+    "adt_comm_scatter_rows": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int32]),
+    "adt_comm_gather_rows": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int32]),
+    "adt_comm_broadcast": (C.c_int, [_P, _P, C.c_size_t, C.c_int32]),
+    "adt_comm_barrier": (C.c_int, [_P]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load():
+    """dlopen the in-tree library and attach prototypes (idempotent)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise AdtError(-1, f"{LIB_PATH} not built; run `make -C pyaudiodsptools_b200/csrc` "
+                                   "or `python -c 'import __graft_entry__ as g; g.build()'`")
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in PROTOTYPES.items():
+                fn = getattr(lib, name)
+                fn.restype, fn.argtypes = res, args
+            _lib = lib
+    return _lib
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    load().adt_device_count(C.byref(n))
+    return n.value
+
+
+def _ptr(a):
+    return None if a is None else (a if isinstance(a, int) else a.ctypes.data)
+
+
+class Context:
+    """One device + one stream (adt_ctx).  All calls check status and raise."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        h = _P()
+        rc = self.lib.adt_ctx_create(device, C.byref(h))
+        if rc != 0:
+            msg = self.lib.adt_status_string(rc).decode()
+            raise AdtError(rc, f"cannot create a context on CUDA device {device}: {msg} "
+                               "(this library has no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def check(self, rc):
+        if rc != 0:
+            raise AdtError(rc, self.lib.adt_last_error(self.h).decode() or self.lib.adt_status_string(rc).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.adt_ctx_destroy(self.h)
+            self.h = None
+
+    # -- memory ------------------------------------------------------------
+    def malloc(self, nbytes: int) -> int:
+        p = _P()
+        self.check(self.lib.adt_malloc(self.h, nbytes, C.byref(p)))
+        return p.value
+
+    def free(self, dptr: int):
+        self.check(self.lib.adt_free(self.h, dptr))
+
+    def pinned_empty(self, shape, dtype=np.float32) -> np.ndarray:
+        """numpy array backed by page-locked host memory (freed with the array)."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = _P()
+        self.check(self.lib.adt_malloc_host(self.h, max(n, 1), C.byref(p)))
+        buf = (C.c_byte * max(n, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        _PINNED[p.value] = (self, buf)
+        import weakref
+        weakref.finalize(buf, _free_pinned, self.lib, self.h, p.value)
+        return arr
+
+    def memset(self, dptr, value, nbytes):
+        self.check(self.lib.adt_memset(self.h, dptr, value, nbytes))
+
+    def h2d(self, dptr: int, host: np.ndarray):
+        host = np.ascontiguousarray(host)
+        self.check(self.lib.adt_memcpy_h2d(self.h, dptr, host.ctypes.data, host.nbytes))
+
+    def d2h(self, host: np.ndarray, dptr: int):
+        assert host.flags["C_CONTIGUOUS"]
+        self.check(self.lib.adt_memcpy_d2h(self.h, host.ctypes.data, dptr, host.nbytes))
+
+    def sync(self):
+        self.check(self.lib.adt_ctx_sync(self.h))
+
+    def launch_count(self) -> int:
+        n = C.c_uint64(0)
+        self.check(self.lib.adt_ctx_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def device_name(self) -> str:
+        buf = C.create_string_buffer(256)
+        self.check(self.lib.adt_ctx_device_name(self.h, buf, 256))
+        return buf.value.decode()
+
+    # -- events ------------------------------------------------------------
+    def event(self):
+        return Event(self)
+
+
+_PINNED = {}
+
+
+def _free_pinned(lib, ctx_h, p):
+    _PINNED.pop(p, None)
+    try:
+        lib.adt_free_host(ctx_h, p)
+    except Exception:
+        pass
+
+
+class Event:
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        h = _P()
+        ctx.check(ctx.lib.adt_event_create(ctx.h, C.byref(h)))
+        self.h = h
+
+    def record(self):
+        self.ctx.check(self.ctx.lib.adt_event_record(self.h))
+
+    def elapsed_ms(self, stop: "Event") -> float:
+        ms = C.c_float(0)
+        self.ctx.check(self.ctx.lib.adt_event_elapsed_ms(self.h, stop.h, C.byref(ms)))
+        return ms.value
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.ctx.lib.adt_event_destroy(self.h)
+        except Exception:
+            pass
+
+
+_contexts = {}
+
+
+def default_context(device: int = 0) -> Context:
+    """Process-wide context per device (what the device classes use)."""
+    with _lock:
+        ctx = _contexts.get(device)
+    if ctx is None:
+        ctx = Context(device)
+        with _lock:
+            _contexts[device] = ctx
+    return ctx

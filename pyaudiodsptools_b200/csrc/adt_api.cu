@@ -1,0 +1,508 @@
+// adt_api.cu — C ABI (include/adt_b200.h): context, memory, events and the
+// FFT FIR engine built on fir_kernel.cuh.  The biquad and the NCCL channel
+// sharding live in adt_biquad.cu / adt_comm.cu.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/adt_b200.h"
+#include "adt_internal.h"
+#define CK ADT_CK
+#include "fir_kernel.cuh"
+#include "fir_tables.h"
+
+using namespace adt;
+
+// ---------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------
+int adt_set_error(adt_ctx* ctx, int status, const char* fmt, ...) {
+    if (ctx) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        ctx->last_error = buf;
+    }
+    return status;
+}
+
+int adt_cuda_fail(adt_ctx* ctx, cudaError_t e, const char* what) {
+    return adt_set_error(ctx, ADT_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+extern "C" const char* adt_version(void) { return "adt_b200 0.1 (sm_100a)"; }
+
+extern "C" const char* adt_status_string(int s) {
+    switch (s) {
+        case ADT_OK: return "ok";
+        case ADT_ERR_INVALID: return "invalid argument";
+        case ADT_ERR_CUDA: return "CUDA error";
+        case ADT_ERR_NO_DEVICE: return "no CUDA device";
+        case ADT_ERR_UNSUPPORTED: return "unsupported geometry";
+        case ADT_ERR_NCCL: return "NCCL error";
+        case ADT_ERR_NOMEM: return "out of memory";
+        default: return "unknown status";
+    }
+}
+
+extern "C" int adt_device_count(int* count) {
+    if (!count) return ADT_ERR_INVALID;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    *count = n;
+    return ADT_OK;
+}
+
+// ---------------------------------------------------------------------------
+// kernel table: one entry per supported transform size
+// ---------------------------------------------------------------------------
+namespace {
+
+typedef void (*fir_kernel_fn)(const FirKernelArgs);
+
+struct FirVariant {
+    int n, threads;
+    size_t smem;
+    fir_kernel_fn cplx, real;
+    std::vector<cf> (*tw1)();
+    std::vector<cf> (*tw2)();
+    std::vector<float> (*permute)(const float*, bool);
+};
+
+template <class C, int MIN_CTAS>
+FirVariant make_variant() {
+    FirVariant v;
+    v.n = C::N;
+    v.threads = C::T;
+    v.smem = fir_smem_bytes<C>();
+    v.cplx = fir_block_kernel<C, cf, MIN_CTAS>;
+    v.real = fir_block_kernel<C, float, MIN_CTAS>;
+    v.tw1 = build_tw1<C>;
+    v.tw2 = build_tw2<C>;
+    v.permute = permute_mask<C>;
+    return v;
+}
+
+const FirVariant* find_variant(int n) {
+    static const FirVariant table[] = {
+        make_variant<FirCfg<16, 8>, 4>(),   // N = 4096,  128 threads
+        make_variant<FirCfg<16, 16>, 2>(),  // N = 8192,  256 threads
+        make_variant<FirCfg<16, 32>, 1>(),  // N = 16384, 512 threads
+    };
+    for (const FirVariant& v : table)
+        if (v.n == n) return &v;
+    return nullptr;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+extern "C" int adt_ctx_create(int device, adt_ctx** out) {
+    if (!out) return ADT_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return ADT_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) return ADT_ERR_INVALID;
+    adt_ctx* ctx = new (std::nothrow) adt_ctx();
+    if (!ctx) return ADT_ERR_NOMEM;
+    ctx->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    for (int i = 0; e == cudaSuccess && i < ADT_COPY_STREAMS; ++i) {
+        e = cudaStreamCreateWithFlags(&ctx->copy_stream[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->copy_done[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->fence, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        delete ctx;
+        return ADT_ERR_CUDA;
+    }
+    for (int nfft : {4096, 8192, 16384}) {
+        const FirVariant* v = find_variant(nfft);
+        for (fir_kernel_fn f : {v->cplx, v->real}) {
+            e = cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->smem);
+            if (e != cudaSuccess) {
+                delete ctx;
+                return ADT_ERR_CUDA;
+            }
+        }
+    }
+    *out = ctx;
+    return ADT_OK;
+}
+
+extern "C" int adt_ctx_destroy(adt_ctx* ctx) {
+    if (!ctx) return ADT_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < ADT_COPY_STREAMS; ++i) {
+        if (ctx->copy_done[i]) cudaEventDestroy(ctx->copy_done[i]);
+        if (ctx->copy_stream[i]) cudaStreamDestroy(ctx->copy_stream[i]);
+    }
+    if (ctx->fence) cudaEventDestroy(ctx->fence);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return ADT_OK;
+}
+
+extern "C" const char* adt_last_error(adt_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+extern "C" int adt_ctx_sync(adt_ctx* ctx) {
+    if (!ctx) return ADT_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return ADT_OK;
+}
+
+extern "C" int adt_ctx_launch_count(adt_ctx* ctx, uint64_t* count) {
+    if (!ctx || !count) return ADT_ERR_INVALID;
+    *count = ctx->launches;
+    return ADT_OK;
+}
+
+extern "C" int adt_ctx_device_name(adt_ctx* ctx, char* buf, size_t len) {
+    if (!ctx || !buf || !len) return ADT_ERR_INVALID;
+    cudaDeviceProp p;
+    CK(ctx, cudaGetDeviceProperties(&p, ctx->device));
+    snprintf(buf, len, "%s (sm_%d%d, %d SMs)", p.name, p.major, p.minor, p.multiProcessorCount);
+    return ADT_OK;
+}
+
+// ---------------------------------------------------------------------------
+// memory
+// ---------------------------------------------------------------------------
+extern "C" int adt_malloc(adt_ctx* ctx, size_t bytes, void** dptr) {
+    if (!ctx || !dptr) return ADT_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMalloc(dptr, bytes ? bytes : 1));
+    return ADT_OK;
+}
+extern "C" int adt_free(adt_ctx* ctx, void* dptr) {
+    if (!ctx) return ADT_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaFree(dptr));
+    return ADT_OK;
+}
+extern "C" int adt_malloc_host(adt_ctx* ctx, size_t bytes, void** hptr) {
+    if (!ctx || !hptr) return ADT_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return ADT_OK;
+}
+extern "C" int adt_free_host(adt_ctx* ctx, void* hptr) {
+    if (!ctx) return ADT_ERR_INVALID;
+    CK(ctx, cudaFreeHost(hptr));
+    return ADT_OK;
+}
+extern "C" int adt_memset(adt_ctx* ctx, void* dptr, int value, size_t bytes) {
+    if (!ctx || (!dptr && bytes)) return ADT_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMemsetAsync(dptr, value, bytes, ctx->stream));
+    return ADT_OK;
+}
+extern "C" int adt_memcpy_h2d(adt_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx || ((!dst || !src) && bytes)) return ADT_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return ADT_OK;
+}
+extern "C" int adt_memcpy_d2h(adt_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx || ((!dst || !src) && bytes)) return ADT_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return ADT_OK;
+}
+extern "C" int adt_memcpy_d2d(adt_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx || ((!dst || !src) && bytes)) return ADT_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return ADT_OK;
+}
+
+// ---------------------------------------------------------------------------
+// events
+// ---------------------------------------------------------------------------
+struct adt_event {
+    adt_ctx* ctx;
+    cudaEvent_t ev;
+};
+
+extern "C" int adt_event_create(adt_ctx* ctx, adt_event** out) {
+    if (!ctx || !out) return ADT_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    adt_event* e = new (std::nothrow) adt_event{ctx, nullptr};
+    if (!e) return ADT_ERR_NOMEM;
+    cudaError_t err = cudaEventCreate(&e->ev);
+    if (err != cudaSuccess) {
+        delete e;
+        return adt_cuda_fail(ctx, err, "cudaEventCreate");
+    }
+    *out = e;
+    return ADT_OK;
+}
+extern "C" int adt_event_destroy(adt_event* ev) {
+    if (!ev) return ADT_ERR_INVALID;
+    cudaEventDestroy(ev->ev);
+    delete ev;
+    return ADT_OK;
+}
+extern "C" int adt_event_record(adt_event* ev) {
+    if (!ev) return ADT_ERR_INVALID;
+    CK(ev->ctx, cudaSetDevice(ev->ctx->device));
+    CK(ev->ctx, cudaEventRecord(ev->ev, ev->ctx->stream));
+    return ADT_OK;
+}
+extern "C" int adt_event_elapsed_ms(adt_event* a, adt_event* b, float* ms) {
+    if (!a || !b || !ms) return ADT_ERR_INVALID;
+    CK(b->ctx, cudaEventSynchronize(b->ev));
+    CK(b->ctx, cudaEventElapsedTime(ms, a->ev, b->ev));
+    return ADT_OK;
+}
+
+// ---------------------------------------------------------------------------
+// FIR engine
+// ---------------------------------------------------------------------------
+struct adt_fir {
+    adt_ctx* ctx = nullptr;
+    adt_fir_desc d{};
+    const FirVariant* var = nullptr;
+    void* d_mask = nullptr;
+    cf* d_tw1 = nullptr;
+    cf* d_tw2 = nullptr;
+    // streaming state: two [n_channels][hist_pitch] buffers (history ++ newest chunk)
+    float* d_hist[2] = {nullptr, nullptr};
+    int cur = 0;
+    int64_t hist_pitch = 0;
+    float* d_io = nullptr;  // [n_channels][chunk] staging for apply_host
+    // scratch for process_host (per copy stream)
+    float* d_in[ADT_COPY_STREAMS] = {};
+    float* d_out[ADT_COPY_STREAMS] = {};
+    size_t in_cap[ADT_COPY_STREAMS] = {};
+    size_t out_cap[ADT_COPY_STREAMS] = {};
+};
+
+static int fir_launch(adt_fir* f, cudaStream_t s, const float* x, int64_t in_pitch, int64_t n_in, int64_t in_shift,
+                      float* y, int64_t out_pitch, int64_t n_out, int32_t n_rows) {
+    adt_ctx* ctx = f->ctx;
+    if (n_rows <= 0 || n_out <= 0) return ADT_OK;
+    const int64_t blocks = (n_out + f->d.hop - 1) / f->d.hop;
+    const int64_t pairs = (n_rows + 1) / 2;
+    if (blocks > 0x7fffffffLL || pairs > 65535)
+        return adt_set_error(ctx, ADT_ERR_UNSUPPORTED, "grid too large: %lld blocks x %lld channel pairs",
+                             (long long)blocks, (long long)pairs);
+    FirKernelArgs a;
+    a.x = x;
+    a.y = y;
+    a.mask = f->d_mask;
+    a.tw1 = f->d_tw1;
+    a.tw2 = f->d_tw2;
+    a.n_rows = n_rows;
+    a.g.hop = f->d.hop;
+    a.g.n0 = f->d.n0;
+    a.g.back = f->d.back;
+    a.g.in_shift = in_shift;
+    a.g.n_in = n_in;
+    a.g.n_out = n_out;
+    a.g.in_pitch = in_pitch;
+    a.g.out_pitch = out_pitch;
+    const dim3 grid((unsigned)blocks, (unsigned)pairs);
+    fir_kernel_fn k = f->d.mask_is_real ? f->var->real : f->var->cplx;
+    k<<<grid, f->var->threads, f->var->smem, s>>>(a);
+    CK(ctx, cudaGetLastError());
+    ctx->launches++;
+    return ADT_OK;
+}
+
+extern "C" int adt_fir_destroy(adt_fir* f) {
+    if (!f) return ADT_ERR_INVALID;
+    cudaSetDevice(f->ctx->device);
+    cudaDeviceSynchronize();
+    cudaFree(f->d_mask);
+    cudaFree(f->d_tw1);
+    cudaFree(f->d_tw2);
+    cudaFree(f->d_hist[0]);
+    cudaFree(f->d_hist[1]);
+    cudaFree(f->d_io);
+    for (int i = 0; i < ADT_COPY_STREAMS; ++i) {
+        cudaFree(f->d_in[i]);
+        cudaFree(f->d_out[i]);
+    }
+    delete f;
+    return ADT_OK;
+}
+
+extern "C" int adt_fir_create(adt_ctx* ctx, const adt_fir_desc* desc, const float* mask, adt_fir** out) {
+    if (!ctx || !desc || !mask || !out) return ADT_ERR_INVALID;
+    *out = nullptr;
+    const FirVariant* var = find_variant(desc->fft_size);
+    if (!var)
+        return adt_set_error(ctx, ADT_ERR_UNSUPPORTED, "fft_size %d not in {4096, 8192, 16384}", desc->fft_size);
+    if (desc->hop < 1 || desc->n0 < 0 || desc->back < 0 || (int64_t)desc->n0 + desc->hop > desc->fft_size)
+        return adt_set_error(ctx, ADT_ERR_INVALID, "bad block geometry: hop=%d n0=%d back=%d N=%d", desc->hop, desc->n0,
+                             desc->back, desc->fft_size);
+    if (desc->chunk < 0 || desc->n_channels < 0 || ((desc->chunk > 0) != (desc->n_channels > 0)))
+        return adt_set_error(ctx, ADT_ERR_INVALID, "chunk and n_channels must both be > 0 or both be 0");
+    CK(ctx, cudaSetDevice(ctx->device));
+    adt_fir* f = new (std::nothrow) adt_fir();
+    if (!f) return ADT_ERR_NOMEM;
+    f->ctx = ctx;
+    f->d = *desc;
+    f->var = var;
+    const std::vector<cf> tw1 = var->tw1(), tw2 = var->tw2();
+    const std::vector<float> pm = var->permute(mask, desc->mask_is_real != 0);
+    cudaError_t e = cudaMalloc(&f->d_mask, pm.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_tw1, tw1.size() * sizeof(cf));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_tw2, tw2.size() * sizeof(cf));
+    if (e == cudaSuccess) e = cudaMemcpy(f->d_mask, pm.data(), pm.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(f->d_tw1, tw1.data(), tw1.size() * sizeof(cf), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(f->d_tw2, tw2.data(), tw2.size() * sizeof(cf), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && desc->n_channels > 0) {
+        f->hist_pitch = ((int64_t)desc->back + desc->chunk + 31) / 32 * 32;
+        const size_t hb = (size_t)desc->n_channels * f->hist_pitch * sizeof(float);
+        for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+            e = cudaMalloc((void**)&f->d_hist[i], hb);
+            if (e == cudaSuccess) e = cudaMemset(f->d_hist[i], 0, hb);
+        }
+        if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_io, (size_t)desc->n_channels * desc->chunk * sizeof(float));
+    }
+    if (e != cudaSuccess) {
+        adt_fir_destroy(f);
+        return adt_cuda_fail(ctx, e, "adt_fir_create");
+    }
+    *out = f;
+    return ADT_OK;
+}
+
+extern "C" int adt_fir_reset(adt_fir* f) {
+    if (!f) return ADT_ERR_INVALID;
+    adt_ctx* ctx = f->ctx;
+    if (!f->d_hist[0]) return ADT_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const size_t hb = (size_t)f->d.n_channels * f->hist_pitch * sizeof(float);
+    CK(ctx, cudaMemsetAsync(f->d_hist[0], 0, hb, ctx->stream));
+    CK(ctx, cudaMemsetAsync(f->d_hist[1], 0, hb, ctx->stream));
+    return ADT_OK;
+}
+
+static int check_buffers(adt_fir* f, const void* x, int64_t in_pitch, int64_t n_in, const void* y, int64_t out_pitch,
+                         int64_t n_out, int32_t n_rows) {
+    if (!f) return ADT_ERR_INVALID;
+    if (n_rows < 0 || n_in < 0 || n_out < 0 || in_pitch < n_in || out_pitch < n_out || ((!x || !y) && n_rows > 0))
+        return adt_set_error(f->ctx, ADT_ERR_INVALID, "bad buffer shape: rows=%d n_in=%lld pitch=%lld n_out=%lld pitch=%lld",
+                             n_rows, (long long)n_in, (long long)in_pitch, (long long)n_out, (long long)out_pitch);
+    return ADT_OK;
+}
+
+extern "C" int adt_fir_process_dev(adt_fir* f, const float* x, int64_t in_pitch, int64_t n_in, float* y,
+                                   int64_t out_pitch, int64_t n_out, int32_t n_rows) {
+    int rc = check_buffers(f, x, in_pitch, n_in, y, out_pitch, n_out, n_rows);
+    if (rc) return rc;
+    CK(f->ctx, cudaSetDevice(f->ctx->device));
+    return fir_launch(f, f->ctx->stream, x, in_pitch, n_in, 0, y, out_pitch, n_out, n_rows);
+}
+
+static int ensure_cap(adt_ctx* ctx, float** p, size_t* cap, size_t need) {
+    if (*cap >= need) return ADT_OK;
+    if (*p) CK(ctx, cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    CK(ctx, cudaMalloc((void**)p, need));
+    *cap = need;
+    return ADT_OK;
+}
+
+extern "C" int adt_fir_process_host(adt_fir* f, const float* x, int64_t in_pitch, int64_t n_in, float* y,
+                                    int64_t out_pitch, int64_t n_out, int32_t n_rows) {
+    int rc = check_buffers(f, x, in_pitch, n_in, y, out_pitch, n_out, n_rows);
+    if (rc) return rc;
+    adt_ctx* ctx = f->ctx;
+    if (n_rows == 0 || n_out == 0) return ADT_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    // row groups of ~48 MB of input, an even number of rows (channel pairs stay together)
+    const int64_t din_pitch = (n_in + 31) / 32 * 32, dout_pitch = (n_out + 31) / 32 * 32;
+    int64_t g_rows = (int64_t)(48u << 20) / (int64_t)((din_pitch > dout_pitch ? din_pitch : dout_pitch) * sizeof(float));
+    g_rows = g_rows < 2 ? 2 : (g_rows & ~1LL);
+    if (g_rows > n_rows) g_rows = (n_rows + 1) & ~1LL;
+    // everything queued on the context stream so far must be done before the copy streams start
+    CK(ctx, cudaEventRecord(ctx->fence, ctx->stream));
+    int gi = 0;
+    for (int64_t r0 = 0; r0 < n_rows; r0 += g_rows, ++gi) {
+        const int si = gi % ADT_COPY_STREAMS;
+        cudaStream_t s = ctx->copy_stream[si];
+        const int32_t rows = (int32_t)((n_rows - r0) < g_rows ? (n_rows - r0) : g_rows);
+        if (gi < ADT_COPY_STREAMS) CK(ctx, cudaStreamWaitEvent(s, ctx->fence, 0));
+        if (f->in_cap[si] < (size_t)g_rows * din_pitch * sizeof(float) ||
+            f->out_cap[si] < (size_t)g_rows * dout_pitch * sizeof(float)) {
+            CK(ctx, cudaStreamSynchronize(s));
+            rc = ensure_cap(ctx, &f->d_in[si], &f->in_cap[si], (size_t)g_rows * din_pitch * sizeof(float));
+            if (rc) return rc;
+            rc = ensure_cap(ctx, &f->d_out[si], &f->out_cap[si], (size_t)g_rows * dout_pitch * sizeof(float));
+            if (rc) return rc;
+        }
+        if (n_in > 0)
+            CK(ctx, cudaMemcpy2DAsync(f->d_in[si], din_pitch * sizeof(float), x + r0 * in_pitch, in_pitch * sizeof(float),
+                                      n_in * sizeof(float), rows, cudaMemcpyHostToDevice, s));
+        rc = fir_launch(f, s, f->d_in[si], din_pitch, n_in, 0, f->d_out[si], dout_pitch, n_out, rows);
+        if (rc) return rc;
+        CK(ctx, cudaMemcpy2DAsync(y + r0 * out_pitch, out_pitch * sizeof(float), f->d_out[si], dout_pitch * sizeof(float),
+                                  n_out * sizeof(float), rows, cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < ADT_COPY_STREAMS; ++i) CK(ctx, cudaStreamSynchronize(ctx->copy_stream[i]));
+    return ADT_OK;
+}
+
+// One streaming step on device buffers: hist[cur] = [last `back` samples | new chunk].
+static int fir_apply_common(adt_fir* f, const float* in, cudaMemcpyKind in_kind, float* out_dev) {
+    adt_ctx* ctx = f->ctx;
+    const int C = f->d.chunk, rows = f->d.n_channels, back = f->d.back;
+    float* cur = f->d_hist[f->cur];
+    float* nxt = f->d_hist[f->cur ^ 1];
+    cudaStream_t s = ctx->stream;
+    CK(ctx, cudaMemcpy2DAsync(cur + back, f->hist_pitch * sizeof(float), in, (size_t)C * sizeof(float),
+                              (size_t)C * sizeof(float), rows, in_kind, s));
+    int rc = fir_launch(f, s, cur, f->hist_pitch, (int64_t)back + C, back, out_dev, C, C, rows);
+    if (rc) return rc;
+    if (back > 0)
+        CK(ctx, cudaMemcpy2DAsync(nxt, f->hist_pitch * sizeof(float), cur + C, f->hist_pitch * sizeof(float),
+                                  (size_t)back * sizeof(float), rows, cudaMemcpyDeviceToDevice, s));
+    f->cur ^= 1;
+    return ADT_OK;
+}
+
+extern "C" int adt_fir_apply_dev(adt_fir* f, const float* in_dev, float* out_dev) {
+    if (!f || !in_dev || !out_dev) return ADT_ERR_INVALID;
+    if (!f->d_hist[0]) return adt_set_error(f->ctx, ADT_ERR_INVALID, "fir was created without streaming state");
+    CK(f->ctx, cudaSetDevice(f->ctx->device));
+    return fir_apply_common(f, in_dev, cudaMemcpyDeviceToDevice, out_dev);
+}
+
+extern "C" int adt_fir_apply_host(adt_fir* f, const float* in_host, float* out_host) {
+    if (!f || !in_host || !out_host) return ADT_ERR_INVALID;
+    if (!f->d_hist[0]) return adt_set_error(f->ctx, ADT_ERR_INVALID, "fir was created without streaming state");
+    adt_ctx* ctx = f->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    int rc = fir_apply_common(f, in_host, cudaMemcpyHostToDevice, f->d_io);
+    if (rc) return rc;
+    CK(ctx, cudaMemcpyAsync(out_host, f->d_io, (size_t)f->d.n_channels * f->d.chunk * sizeof(float),
+                            cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return ADT_OK;
+}

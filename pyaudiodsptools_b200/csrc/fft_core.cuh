@@ -1,0 +1,365 @@
+// fft_core.cuh — register-resident radix-16/32 FFT building blocks and the
+// per-thread phases of the fused overlap-save FIR block
+//     window -> FFT_N -> x mask -> IFFT_N -> slice
+// for TWO real channels packed as one complex signal (re = channel a,
+// im = channel b; valid because the taps are real, so no split/merge pass).
+//
+// Replaces the per-chunk numpy pipeline of the reference
+//     pyAudioDspTools/EffectFFTFilter.py:143-151   (concatenate, fft, *mask, ifft, slice)
+//     pyAudioDspTools/EffectEQ3BandFFT.py:175-211  (1 fft + 3 masked iffts + mix)
+// by one N-point complex transform pair per (block, channel pair); the
+// equivalence is SURVEY.md Appendix A.3/A.4 and DESIGN.md §2.
+//
+// Decomposition  N = N1 * N2 * 32,  T = N/32 threads, 32 complex points per
+// thread held in registers through every stage.  M1 = N/N1 = N2*32.
+//
+//   stage 1 (thread r, B1=32/N1 butterflies): DFT_N1 over n1 of x[n1*M1 + r],
+//            times W_N^(r*k1)                      -> A[k1][r]
+//   stage 2 (thread (k1, r2=lane), B2=32/N2):  DFT_N2 over n2 of A[k1][n2*32+r2],
+//            times W_M1^(r2*k2)                    -> B[k1][k2][r2]
+//   stage 3 (thread t = k1*N2 + k2):           DFT_32 over r2
+//            -> X[k1 + N1*k2 + T*k3]   (natural order, stride T across k3)
+//   mask multiply in registers, then the mirror image (DIT, conjugate
+//   twiddles applied on input) back to y[n1*M1 + r].
+//
+// Shared memory holds one [T rows][33] float2 tile; every exchange is done
+// IN PLACE (each thread writes exactly the addresses it read last), so only
+// the four read-after-write barriers per block are needed.  Row pitch 33
+// makes both the row-wise (stage 3) and column-wise (stages 1,2) accesses
+// bank-conflict free with immediate offsets.
+//
+// All functions are __host__ __device__: tests/emu/ runs the very same code
+// on the CPU with a loop over thread ids to validate the index algebra
+// without a GPU (development check only — never a product path).
+#pragma once
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ADT_HD __host__ __device__ __forceinline__
+#define ADT_ALIGN8 __align__(8)
+#else
+#define ADT_HD inline __attribute__((always_inline))
+#define ADT_ALIGN8 alignas(8)
+#endif
+
+namespace adt {
+
+struct ADT_ALIGN8 cf {
+    float x, y;
+};
+
+ADT_HD cf cmul(cf a, cf b) { return cf{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+// a * conj(b)
+ADT_HD cf cmulc(cf a, cf b) { return cf{a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y}; }
+
+ADT_HD cf mask_mul(cf a, float h) { return cf{a.x * h, a.y * h}; }  // zero-phase (real) mask
+ADT_HD cf mask_mul(cf a, cf h) { return cmul(a, h); }
+
+// cos / sin of 2*pi*q/32 as literals (constexpr trig is not available).
+ADT_HD constexpr float cos32(int q) {
+    switch (q & 31) {
+        case 0: return 1.0f;
+        case 1: case 31: return 0.98078528040323043f;
+        case 2: case 30: return 0.92387953251128674f;
+        case 3: case 29: return 0.83146961230254524f;
+        case 4: case 28: return 0.70710678118654752f;
+        case 5: case 27: return 0.55557023301960218f;
+        case 6: case 26: return 0.38268343236508977f;
+        case 7: case 25: return 0.19509032201612825f;
+        case 8: case 24: return 0.0f;
+        case 9: case 23: return -0.19509032201612825f;
+        case 10: case 22: return -0.38268343236508977f;
+        case 11: case 21: return -0.55557023301960218f;
+        case 12: case 20: return -0.70710678118654752f;
+        case 13: case 19: return -0.83146961230254524f;
+        case 14: case 18: return -0.92387953251128674f;
+        case 15: case 17: return -0.98078528040323043f;
+        default: return -1.0f;  // 16
+    }
+}
+ADT_HD constexpr float sin32(int q) { return cos32(q - 8); }
+
+template <int R>
+ADT_HD constexpr int brev(int i) {
+    int r = 0;
+    for (int b = 1, c = R >> 1; c; b <<= 1, c >>= 1)
+        if (i & b) r |= c;
+    return r;
+}
+
+// DIT butterfly  a' = a + W b,  b' = a - W b,  W = exp(DIR * 2*pi*i * Q/32).
+// DIR = -1: forward transform, +1: inverse.  Q in [0, 16).
+template <int Q, int DIR>
+ADT_HD void bfly(cf& a, cf& b) {
+    if constexpr (Q == 0) {
+        const cf t = b;
+        b = cf{a.x - t.x, a.y - t.y};
+        a = cf{a.x + t.x, a.y + t.y};
+    } else if constexpr (Q == 8) {
+        // W = i*DIR :  W b = (-DIR*b.y, DIR*b.x)
+        const cf t = b;
+        if constexpr (DIR < 0) {
+            b = cf{a.x - t.y, a.y + t.x};
+            a = cf{a.x + t.y, a.y - t.x};
+        } else {
+            b = cf{a.x + t.y, a.y - t.x};
+            a = cf{a.x - t.y, a.y + t.x};
+        }
+    } else if constexpr (Q == 4) {
+        // W = c*(1 + i*DIR):  W b = c*(b.x - DIR*b.y, b.y + DIR*b.x)
+        constexpr float c = 0.70710678118654752f;
+        const float s = (DIR < 0) ? (b.x + b.y) : (b.x - b.y);
+        const float d = (DIR < 0) ? (b.y - b.x) : (b.y + b.x);
+        b = cf{a.x - c * s, a.y - c * d};
+        a = cf{a.x + c * s, a.y + c * d};
+    } else if constexpr (Q == 12) {
+        // W = c*(-1 + i*DIR): W b = c*(-b.x - DIR*b.y, -b.y + DIR*b.x)
+        constexpr float c = 0.70710678118654752f;
+        const float s = (DIR < 0) ? (b.y - b.x) : (-b.x - b.y);
+        const float d = (DIR < 0) ? (-b.y - b.x) : (b.x - b.y);
+        b = cf{a.x - c * s, a.y - c * d};
+        a = cf{a.x + c * s, a.y + c * d};
+    } else {
+        constexpr float wr = cos32(Q);
+        constexpr float wi = (DIR < 0) ? -sin32(Q) : sin32(Q);
+        const float tr = wr * b.x - wi * b.y;
+        const float ti = wr * b.y + wi * b.x;
+        b = cf{a.x - tr, a.y - ti};
+        a = cf{a.x + tr, a.y + ti};
+    }
+}
+
+template <int R, int DIR, int HALF, int I>
+ADT_HD void dft_step(cf* v) {
+    if constexpr (I < R) {
+        if constexpr ((I & HALF) == 0) {
+            constexpr int j = I & (HALF - 1);
+            constexpr int q = j * 16 / HALF;
+            bfly<q, DIR>(v[brev<R>(I)], v[brev<R>(I + HALF)]);
+        }
+        dft_step<R, DIR, HALF, I + 1>(v);
+    }
+}
+template <int R, int DIR, int HALF>
+ADT_HD void dft_stage(cf* v) {
+    if constexpr (HALF < R) {
+        dft_step<R, DIR, HALF, 0>(v);
+        dft_stage<R, DIR, HALF * 2>(v);
+    }
+}
+// In-place R-point DFT (R = 2..32) on a register array.
+// Input x[n] at v[n]; output X[k] at v[brev<R>(k)].
+template <int R, int DIR>
+ADT_HD void dft(cf* v) {
+    dft_stage<R, DIR, 1>(v);
+}
+
+// compile-time loop: f receives an IC<i>; read the index as decltype(K)::value
+template <int I>
+struct IC {
+    static constexpr int value = I;
+};
+template <int B, int E, class F>
+ADT_HD void static_for(F&& f) {
+    if constexpr (B < E) {
+        f(IC<B>{});
+        static_for<B + 1, E>(f);
+    }
+}
+ADT_HD constexpr int hibit(int k) {  // largest power of two <= k
+    int h = 1;
+    while (h * 2 <= k) h *= 2;
+    return h;
+}
+
+// Powers w^1..w^(R-1) of a unit-modulus base by a depth-log2(R) product tree
+// (w^k from w^(k - p) * w^p with p the highest power of two below k ... ),
+// then multiply v[brev(k)] by them.  CONJ selects conj(w^k).
+template <int R, bool CONJ>
+ADT_HD void apply_powers(cf* v, cf w1) {
+    cf p[R];
+    p[1] = w1;
+    static_for<2, R>([&](auto K) {
+        constexpr int k = decltype(K)::value;
+        constexpr int hi = (k & (k - 1)) == 0 ? k / 2 : hibit(k);
+        constexpr int lo = k - hi;
+        p[k] = cmul(p[hi], p[lo]);
+    });
+    static_for<1, R>([&](auto K) {
+        constexpr int k = decltype(K)::value;
+        if constexpr (CONJ)
+            v[k] = cmulc(v[k], p[k]);
+        else
+            v[brev<R>(k)] = cmul(v[brev<R>(k)], p[k]);
+    });
+}
+
+// ---------------------------------------------------------------------------
+// configuration of one transform size
+// ---------------------------------------------------------------------------
+template <int N1_, int N2_>
+struct FirCfg {
+    static constexpr int N1 = N1_, N2 = N2_, N3 = 32;
+    static constexpr int N = N1 * N2 * 32;
+    static constexpr int T = N1 * N2;        // threads per CTA (= rows of the tile)
+    static constexpr int M1 = N2 * 32;       // size of the sub-transform after stage 1
+    static constexpr int B1 = 32 / N1;       // stage-1 butterflies per thread
+    static constexpr int B2 = 32 / N2;       // stage-2 butterflies per thread
+    static constexpr int PITCH = 33;         // float2 per tile row
+    static constexpr int TILE = T * PITCH;   // float2 elements of shared memory
+    static constexpr int WARPS = T / 32;
+};
+
+// What one FIR block needs to know (see DESIGN.md §3 for the derivation).
+struct FirGeom {
+    int hop;         // outputs produced per block
+    int n0;          // first kept index of the N-point circular result
+    int back;        // window of block b starts at stream index b*hop - back + in_shift
+    long long in_shift;
+    long long n_in;  // valid input samples per row (others read as 0)
+    long long n_out; // outputs wanted per row
+    long long in_pitch, out_pitch;  // row pitches in floats
+};
+
+// ---- phase 0: global -> registers (stage-1 layout) -------------------------
+template <class C>
+ADT_HD void load_window(cf* v, int t, const float* __restrict__ xa, const float* __restrict__ xb,
+                        long long ws, long long n_in) {
+    const bool interior = (ws >= 0) && (ws + C::N <= n_in);
+    if (interior) {
+        static_for<0, C::B1>([&](auto U) {
+            static_for<0, C::N1>([&](auto K) {
+                constexpr int u = decltype(U)::value, n1 = decltype(K)::value;
+                const long long s = ws + n1 * C::M1 + t + u * C::T;
+                v[u * C::N1 + n1] = cf{xa[s], xb ? xb[s] : 0.0f};
+            });
+        });
+    } else {
+        static_for<0, C::B1>([&](auto U) {
+            static_for<0, C::N1>([&](auto K) {
+                constexpr int u = decltype(U)::value, n1 = decltype(K)::value;
+                const long long s = ws + n1 * C::M1 + t + u * C::T;
+                const bool ok = (s >= 0) && (s < n_in);
+                v[u * C::N1 + n1] = cf{ok ? xa[s] : 0.0f, (ok && xb) ? xb[s] : 0.0f};
+            });
+        });
+    }
+}
+
+// ---- phase 1: forward stage 1, write tile ----------------------------------
+template <class C>
+ADT_HD void fwd_stage1(cf* v, int t, const cf* __restrict__ tw1, cf* tile) {
+    const int lane = t & 31;
+    static_for<0, C::B1>([&](auto U) {
+        constexpr int u = decltype(U)::value;
+        cf* b = v + u * C::N1;
+        dft<C::N1, -1>(b);
+        const int r = t + u * C::T;
+        apply_powers<C::N1, false>(b, tw1[r]);
+        const int row0 = r >> 5;  // n2
+        static_for<0, C::N1>([&](auto K) {
+            constexpr int k1 = decltype(K)::value;
+            tile[(k1 * C::N2 + row0) * C::PITCH + lane] = b[brev<C::N1>(k1)];
+        });
+    });
+}
+
+// ---- phase 2: forward stage 2, in place in the tile --------------------------
+template <class C>
+ADT_HD void fwd_stage2(cf* v, int t, const cf* __restrict__ tw2, cf* tile) {
+    const int lane = t & 31, warp = t >> 5;
+    static_for<0, C::B2>([&](auto U) {
+        constexpr int u = decltype(U)::value;
+        cf* b = v + u * C::N2;
+        cf* col = tile + ((warp + u * C::WARPS) * C::N2) * C::PITCH + lane;
+        static_for<0, C::N2>([&](auto K) { constexpr int n2 = decltype(K)::value; b[n2] = col[n2 * C::PITCH]; });
+        dft<C::N2, -1>(b);
+        static_for<0, C::N2>([&](auto K) {
+            constexpr int k2 = decltype(K)::value;
+            cf val = b[brev<C::N2>(k2)];
+            if constexpr (k2 > 0) val = cmul(val, tw2[k2 * 32 + lane]);
+            col[k2 * C::PITCH] = val;
+        });
+    });
+}
+
+// ---- phase 3: forward DFT32, mask, inverse DFT32, in place row t ------------
+template <class C, class MaskT>
+ADT_HD void mid_stage3(cf* v, int t, const MaskT* __restrict__ mask, cf* tile) {
+    cf* row = tile + t * C::PITCH;
+    static_for<0, 32>([&](auto K) { constexpr int r2 = decltype(K)::value; v[r2] = row[r2]; });
+    dft<32, -1>(v);
+    cf y[32];
+    static_for<0, 32>([&](auto K) {
+        constexpr int k3 = decltype(K)::value;
+        const cf x = v[brev<32>(k3)];
+        y[k3] = mask_mul(x, mask[k3 * C::T + t]);
+    });
+    dft<32, +1>(y);
+    static_for<0, 32>([&](auto K) { constexpr int r2 = decltype(K)::value; row[r2] = y[brev<32>(r2)]; });
+}
+
+// ---- phase 4: inverse stage 2 (conj twiddle on input), in place --------------
+template <class C>
+ADT_HD void inv_stage2(cf* v, int t, const cf* __restrict__ tw2, cf* tile) {
+    const int lane = t & 31, warp = t >> 5;
+    static_for<0, C::B2>([&](auto U) {
+        constexpr int u = decltype(U)::value;
+        cf* b = v + u * C::N2;
+        cf* col = tile + ((warp + u * C::WARPS) * C::N2) * C::PITCH + lane;
+        static_for<0, C::N2>([&](auto K) {
+            constexpr int k2 = decltype(K)::value;
+            cf val = col[k2 * C::PITCH];
+            if constexpr (k2 > 0) val = cmulc(val, tw2[k2 * 32 + lane]);
+            b[k2] = val;
+        });
+        dft<C::N2, +1>(b);
+        static_for<0, C::N2>([&](auto K) { constexpr int n2 = decltype(K)::value; col[n2 * C::PITCH] = b[brev<C::N2>(n2)]; });
+    });
+}
+
+// ---- phase 5: inverse stage 1, results stay in registers --------------------
+// On return v[u*N1 + brev(n1)] = z[n1*M1 + t + u*T].
+template <class C>
+ADT_HD void inv_stage1(cf* v, int t, const cf* __restrict__ tw1, const cf* tile) {
+    const int lane = t & 31;
+    static_for<0, C::B1>([&](auto U) {
+        constexpr int u = decltype(U)::value;
+        cf* b = v + u * C::N1;
+        const int r = t + u * C::T;
+        const int row0 = r >> 5;
+        static_for<0, C::N1>([&](auto K) {
+            constexpr int k1 = decltype(K)::value;
+            b[k1] = tile[(k1 * C::N2 + row0) * C::PITCH + lane];
+        });
+        apply_powers<C::N1, true>(b, tw1[r]);
+        dft<C::N1, +1>(b);
+    });
+}
+
+// ---- phase 6: registers -> global (only the valid slice) -------------------
+// z[n], n = n1*M1 + t + u*T, goes to y[m0 + n - n0] when 0 <= n - n0 < hop and
+// the stream index is below n_out.  `lim` = min(hop, n_out - m0) folds both
+// upper bounds into one unsigned compare per element.
+template <class C>
+ADT_HD void store_slice(const cf* v, int t, float* __restrict__ ya, float* __restrict__ yb,
+                        long long m0, const FirGeom& g) {
+    const long long room = g.n_out - m0;
+    const unsigned lim = (unsigned)(room < (long long)g.hop ? (room < 0 ? 0 : room) : g.hop);
+    float* pa = ya + (m0 - g.n0) + t;
+    float* pb = yb ? yb + (m0 - g.n0) + t : nullptr;
+    const int jt = t - g.n0;
+    static_for<0, C::B1>([&](auto U) {
+        static_for<0, C::N1>([&](auto K) {
+            constexpr int u = decltype(U)::value, n1 = decltype(K)::value;
+            constexpr int off = n1 * C::M1 + u * C::T;
+            const cf z = v[u * C::N1 + brev<C::N1>(n1)];
+            const bool ok = (unsigned)(jt + off) < lim;
+            if (ok) pa[off] = z.x;
+            if (ok && pb) pb[off] = z.y;
+        });
+    });
+}
+
+}  // namespace adt

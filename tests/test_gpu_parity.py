@@ -1,0 +1,213 @@
+"""GPU tier: the CUDA path (through the C ABI) against the golden vectors of
+the live reference and against the oracle.  Tolerance (north_star): RMS error
+<= 1e-5 on float32 chunks; we assert 2e-6 (measured ~2e-7) so regressions show.
+"""
+import numpy as np
+import pytest
+
+import oracle
+import pyaudiodsptools_b200 as adt
+from conftest import golden_fft_cases, load_golden, rms
+
+pytestmark = pytest.mark.gpu
+
+RMS_TOL = 2e-6      # north_star allows 1e-5
+MAX_TOL = 2e-5
+
+
+def _make(meta, **kw):
+    adt.config.initialize(meta["fs"], meta["chunk"])
+    ctor = {"lowcut": adt.CreateLowCutFilter, "highcut": adt.CreateHighCutFilter, "eq3fft": adt.CreateEQ3BandFFT}
+    return ctor[meta["kind"]](*meta["args"], **kw)
+
+
+def _supported(meta):
+    return not (meta["kind"] == "eq3fft" and meta["chunk"] > 8192)
+
+
+@pytest.mark.parametrize("name", golden_fft_cases())
+def test_streaming_apply_matches_reference(gpu_lib, name):
+    meta, arr = load_golden(name)
+    if not _supported(meta):
+        pytest.skip("EQ at this chunk size needs FFT > 16384")
+    dev = _make(meta)
+    c = meta["chunk"]
+    outs = [dev.apply(arr["x"][i:i + c]) for i in range(0, len(arr["x"]), c)]
+    assert all(o.dtype == np.float32 and o.shape == (c,) for o in outs)
+    y = np.concatenate(outs)
+    assert rms(y - arr["y"]) <= RMS_TOL
+    assert np.max(np.abs(y - arr["y"])) <= MAX_TOL
+
+
+@pytest.mark.parametrize("name", golden_fft_cases())
+def test_whole_buffer_matches_reference(gpu_lib, name):
+    meta, arr = load_golden(name)
+    if not _supported(meta):
+        pytest.skip("EQ at this chunk size needs FFT > 16384")
+    dev = _make(meta)
+    y = dev.process(arr["x"])
+    assert y.shape == arr["y"].shape
+    assert rms(y - arr["y"]) <= RMS_TOL
+    assert np.max(np.abs(y - arr["y"])) <= MAX_TOL
+
+
+@pytest.mark.parametrize("fft_size", [4096, 8192, 16384])
+@pytest.mark.parametrize("name", ["highcut4000_c512_noise", "eq3fft_c512_noise", "lowcut160_default_c1024_noise"])
+def test_every_kernel_size(gpu_lib, name, fft_size):
+    meta, arr = load_golden(name)
+    dev = _make(meta, fft_size=fft_size)
+    assert dev.plan.fft_size == fft_size
+    y = dev.process(arr["x"])
+    assert rms(y - arr["y"]) <= RMS_TOL
+    c = meta["chunk"]
+    ys = np.concatenate([dev.apply(arr["x"][i:i + c]) for i in range(0, len(arr["x"]), c)])
+    assert rms(ys - arr["y"]) <= RMS_TOL
+
+
+@pytest.mark.parametrize("channels", [1, 2, 5, 64])
+def test_batched_channels_are_independent(gpu_lib, channels):
+    fs, c, n = 44100, 1024, 7 * 1024 + 300     # ragged tail: MakeChunks zero-pads
+    adt.config.initialize(fs, c)
+    dev = adt.CreateLowCutFilter(800, channels=channels)
+    x = np.stack([np.random.default_rng(100 + ch).uniform(-1, 1, n).astype(np.float32) for ch in range(channels)])
+    y = dev.process(x)
+    assert y.shape == (channels, 8 * c)
+    taps = oracle.lowcut_taps(fs, c, 800)
+    for ch in range(channels):
+        want = oracle.fir_stream_f64(taps, c, x[ch])
+        assert rms(y[ch] - want) <= RMS_TOL, ch
+    # streaming with a batch: [channels, C] in, [channels, C] out
+    xp = np.pad(x, ((0, 0), (0, 8 * c - n)))
+    ys = np.concatenate([dev.apply(xp[:, i:i + c]).reshape(channels, c) for i in range(0, 8 * c, c)], axis=1)
+    assert rms(ys - y) <= 1e-6
+
+
+def test_eq_batched_stereo_pairs(gpu_lib):
+    # BASELINE config 5 shape in miniature: 96 kHz, stereo = two planar rows per stream
+    fs, c = 96000, 4096
+    adt.config.initialize(fs, c)
+    dev = adt.CreateLowCutFilter(800, channels=6)
+    x = np.random.default_rng(9).uniform(-1, 1, (6, 5 * c)).astype(np.float32)
+    y = dev.process(x)
+    taps = oracle.lowcut_taps(fs, c, 800)
+    for ch in range(6):
+        assert rms(y[ch] - oracle.fir_stream_f64(taps, c, x[ch])) <= RMS_TOL
+
+
+def test_first_calls_and_latency(gpu_lib):
+    # call 0 returns (almost) silence: only the pre-ring of chunk 0 in its last C/4-1 samples
+    adt.config.initialize(44100, 512)
+    dev = adt.CreateHighCutFilter(4000)
+    x = np.zeros(512, dtype=np.float32); x[0] = 1.0
+    y0 = dev.apply(x)
+    assert not y0[: 512 - 127].any() and y0[512 - 127:].any()
+    y1 = dev.apply(np.zeros(512, dtype=np.float32))
+    taps = oracle.highcut_taps(44100, 512, 4000)
+    full = np.concatenate([y0, y1])
+    d = oracle.stream_delay(512)
+    assert rms(full[d:d + len(taps)] - taps) <= 1e-7      # impulse response == taps at delay D
+    dev.reset()
+    assert np.array_equal(dev.apply(x), y0)
+
+
+def test_wrong_length_raises_and_keeps_state(gpu_lib):
+    adt.config.initialize(44100, 512)
+    a, b = adt.CreateLowCutFilter(300), adt.CreateLowCutFilter(300)
+    x = np.random.default_rng(3).uniform(-1, 1, 3 * 512).astype(np.float32)
+    a.apply(x[:512]); b.apply(x[:512])
+    with pytest.raises(ValueError):
+        a.apply(x[:100])
+    assert np.array_equal(a.apply(x[512:1024]), b.apply(x[512:1024]))   # history untouched by the failed call
+
+
+def test_array_likes_accepted(gpu_lib):
+    adt.config.initialize(44100, 512)
+    a, b, c = adt.CreateHighCutFilter(4000), adt.CreateHighCutFilter(4000), adt.CreateHighCutFilter(4000)
+    x = np.random.default_rng(4).uniform(-1, 1, 512).astype(np.float32)
+    ya = a.apply(x)
+    assert np.array_equal(ya, b.apply(x.reshape(2, 256)))      # concatenate(axis=None) flattens
+    assert np.array_equal(ya, c.apply(list(x)))
+
+
+def test_linearity_and_shift_invariance_large(gpu_lib):
+    # size-independent properties at a BASELINE-sized chunk: 64 channels x 10 s, C = 4096
+    fs, c, n = 44100, 4096, 441000
+    adt.config.initialize(fs, c)
+    dev = adt.CreateLowCutFilter(800, channels=64)
+    rng = np.random.default_rng(11)
+    a = rng.uniform(-1, 1, (64, n)).astype(np.float32)
+    b = rng.uniform(-1, 1, (64, n)).astype(np.float32)
+    ya, yb, yab = dev.process(a), dev.process(b), dev.process(a + 0.5 * b)
+    assert rms(yab - (ya + 0.5 * yb)) <= 2e-6
+    shifted = np.zeros_like(a); shifted[:, 4096:] = a[:, :-4096]
+    ys = dev.process(shifted)
+    assert rms(ys[:, 4096:] - ya[:, :-4096]) <= 2e-6
+    taps = oracle.lowcut_taps(fs, c, 800)
+    for ch in (0, 31, 63):
+        from scipy.signal import fftconvolve
+        full = fftconvolve(a[ch].astype(np.float64), taps)
+        want = np.zeros(ya.shape[1]); d = oracle.stream_delay(c)
+        want[d:] = full[: ya.shape[1] - d]
+        assert rms(ya[ch] - want) <= RMS_TOL
+
+
+def test_device_resident_whole_buffer(gpu_lib):
+    fs, c, rows, n = 44100, 4096, 9, 5 * 4096
+    adt.config.initialize(fs, c)
+    dev = adt.CreateEQ3BandFFT(100, 2, 700, -4, 8000, 5, channels=rows)
+    ctx = dev.context
+    x = np.random.default_rng(5).uniform(-1, 1, (rows, n)).astype(np.float32)
+    dx, dy = ctx.malloc(x.nbytes), ctx.malloc(x.nbytes)
+    ctx.h2d(dx, x)
+    before = ctx.launch_count()
+    dev.process_device(dx, n, n, dy, n, n, rows)
+    ctx.sync()
+    assert ctx.launch_count() == before + 1
+    y = np.empty_like(x)
+    ctx.d2h(y, dy)
+    ctx.free(dx); ctx.free(dy)
+    taps = oracle.eq3_composite_taps(fs, c, 100, 2, 700, -4, 8000, 5)
+    for ch in range(rows):
+        assert rms(y[ch] - oracle.fir_stream_f64(taps, c, x[ch])) <= RMS_TOL
+
+
+def test_capi_rejects_bad_geometry(gpu_lib):
+    import ctypes as C
+    from pyaudiodsptools_b200 import _native
+    ctx = _native.default_context(0)
+    mask = np.zeros(2 * 8192, dtype=np.float32)
+    h = C.c_void_p()
+    for desc in (_native.FirDesc(1000, 10, 0, 0, 0, 0, 0, 0),       # unsupported N
+                 _native.FirDesc(8192, 8000, 500, 0, 0, 0, 0, 0),   # n0 + hop > N
+                 _native.FirDesc(8192, 64, 0, 0, 0, 512, 0, 0)):    # chunk without channels
+        rc = gpu_lib.adt_fir_create(ctx.h, C.byref(desc), mask.ctypes.data, C.byref(h))
+        assert rc in (-1, -4) and not h.value
+        assert gpu_lib.adt_last_error(ctx.h)
+
+
+# ---- the streaming biquad: bit-exact ---------------------------------------------
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_biquad_bit_exact(gpu_lib, tag):
+    meta, arr = load_golden("eq3biquad_" + tag)
+    blk, x = meta["block"], arr["x"]
+    eq, eq2 = adt.CreateEQ3Band(*meta["args"]), adt.CreateEQ3Band(*meta["args"])
+    outs = {"low": [], "mid": [], "high": [], "chain": []}
+    for i in range(0, len(x), blk):
+        b = x[i:i + blk]
+        outs["low"].append(eq.applylowband(b)); outs["mid"].append(eq.applymidband(b))
+        outs["high"].append(eq.applyhighband(b)); outs["chain"].append(eq2.apply(b))
+    for k, v in outs.items():
+        got = np.concatenate(v)
+        assert got.dtype == arr[k].dtype
+        np.testing.assert_array_equal(got, arr[k])
+
+
+def test_biquad_batched_channels(gpu_lib):
+    chans, n = 70, 1000     # not a multiple of 32 channels, ragged time tile
+    eq = adt.CreateEQ3Band(100, 2, 700, -4, 8000, 5, channels=chans)
+    x = np.random.default_rng(8).uniform(-1, 1, (chans, 2 * n)).astype(np.float32)
+    y = np.concatenate([eq.applymidband(x[:, :n]), eq.applymidband(x[:, n:])], axis=1)
+    for ch in (0, 31, 32, 69):
+        o = oracle.Eq3BandBiquad(100, 2, 700, -4, 8000, 5)
+        want = np.concatenate([o.applymidband(x[ch, :n].copy()), o.applymidband(x[ch, n:].copy())])
+        np.testing.assert_array_equal(y[ch], want)

@@ -1,0 +1,132 @@
+"""CPU tier: host-side logic of the product (no GPU, no compute calls into the .so)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+import pyaudiodsptools_b200 as adt
+from pyaudiodsptools_b200 import _native, design, devices
+from conftest import ROOT, golden_fft_cases, load_golden, rms
+
+
+def _taps_for(meta):
+    fs, c, a = meta["fs"], meta["chunk"], meta["args"]
+    if meta["kind"] == "lowcut":
+        return design.lowcut_taps(fs, c, a[0] if a else 160)
+    if meta["kind"] == "highcut":
+        return design.highcut_taps(fs, c, a[0] if a else 8000)
+    return design.eq3_taps(fs, c, *a)
+
+
+def _overlap_save_numpy(plan, x, n_out):
+    """What the CUDA engine computes, in float64 numpy, from the plan alone."""
+    n, hop, n0, back = plan.fft_size, plan.hop, plan.n0, plan.back
+    y = np.zeros(n_out)
+    mask = plan.mask.astype(np.complex128)
+    for b in range(-(-n_out // hop)):
+        ws = b * hop - back
+        idx = ws + np.arange(n)
+        ok = (idx >= 0) & (idx < len(x))
+        w = np.where(ok, x[np.clip(idx, 0, len(x) - 1)], 0.0)
+        z = np.fft.ifft(np.fft.fft(w) * mask).real
+        m0 = b * hop
+        k = min(hop, n_out - m0)
+        y[m0:m0 + k] = z[n0:n0 + k]
+    return y
+
+
+@pytest.mark.parametrize("name", golden_fft_cases())
+def test_block_plan_reproduces_reference(name):
+    meta, arr = load_golden(name)
+    if meta["chunk"] > 8192 and meta["kind"] == "eq3fft":
+        pytest.skip("needs an FFT larger than this build supports")
+    plan = design.plan_block(_taps_for(meta), design.stream_delay(meta["chunk"]))
+    assert plan.n0 % 32 == 0 and plan.hop % 32 == 0 and plan.back % 32 == 0
+    assert plan.n0 + plan.hop <= plan.fft_size
+    y = _overlap_save_numpy(plan, arr["x"].astype(np.float64), len(arr["y"]))
+    assert rms(y - arr["y"]) <= 1e-7          # complex64 mask rounding + the reference's own noise
+    assert np.max(np.abs(y - arr["y"])) <= 2e-6
+
+
+@pytest.mark.parametrize("fft_size", [4096, 8192, 16384])
+def test_block_plan_any_fft_size(fft_size):
+    meta, arr = load_golden("highcut4000_c1024_noise")
+    plan = design.plan_block(_taps_for(meta), design.stream_delay(1024), fft_size)
+    assert plan.mask_is_real and plan.fft_size == fft_size
+    y = _overlap_save_numpy(plan, arr["x"].astype(np.float64), len(arr["y"]))
+    assert rms(y - arr["y"]) <= 1e-7
+
+
+def test_design_equals_oracle_design():
+    for c in (512, 1024, 4096, 16384):
+        assert np.array_equal(design.lowcut_taps(44100, c, 800), oracle.lowcut_taps(44100, c, 800))
+        assert np.array_equal(design.highcut_taps(96000, c, 4000), oracle.highcut_taps(96000, c, 4000))
+        a = design.eq3_taps(44100, c, 100, 2, 700, -4, 8000, 5)
+        b = oracle.eq3_composite_taps(44100, c, 100, 2, 700, -4, 8000, 5)
+        assert np.max(np.abs(a - b)) <= 1e-15
+        assert design.stream_delay(c) == oracle.stream_delay(c) == 3 * c // 4 + 1
+
+
+def test_eq_too_large_is_rejected():
+    with pytest.raises(ValueError):
+        design.plan_block(np.ones(16381), design.stream_delay(16384))
+
+
+def test_biquad_coefficients_match_oracle():
+    from oracle.biquad import band_coefficients
+    for args in ((100, 2, 700, -4, 8000, 5), (250, -6, 1200, 3, 6000, -2), (80, 0, 1000, 0, 10000, 0)):
+        for (b0, b1, b2, a0, a1, a2), got in zip(band_coefficients(*args), devices.biquad_coefficients(*args)):
+            assert tuple(got) == (b0 / a0, b1 / a0, b2 / a0, a1 / a0, a2 / a0)
+
+
+def test_config_mirror():
+    adt.config.initialize(48000, 256)
+    assert (adt.config.sampling_rate, adt.config.chunk_size, adt.config.use_gpu) == (48000, 256, False)
+    adt.config.initialize(44100, 512, use_gpu=True)
+    assert adt.config.use_gpu is True
+    adt.config.sampling_rate = None
+    with pytest.raises(TypeError):
+        adt.CreateLowCutFilter(800)
+    adt.config.initialize(44100, 512)
+
+
+def test_make_and_combine_chunks():
+    adt.config.initialize(44100, 512)
+    x = np.arange(1300, dtype=np.float32)
+    chunks = adt.MakeChunks(x)
+    assert len(chunks) == 3 and all(len(c) == 512 for c in chunks)
+    back = adt.CombineChunks(chunks)
+    assert back.dtype == np.float32 and np.array_equal(back[:1300], x) and not back[1300:].any()
+    assert len(adt.MakeChunks(np.zeros(1024, dtype=np.float32))) == 2
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "adt_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)      # declarations only, not prose
+    declared = set(re.findall(r"\b(adt_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_native.PROTOTYPES), declared ^ set(_native.PROTOTYPES)
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _native.load().adt_version().startswith(b"adt_b200")
+
+
+def test_no_cpu_fallback_without_device():
+    if _native.device_count() > 0:
+        pytest.skip("a GPU is present")
+    adt.config.initialize(44100, 512)
+    with pytest.raises(adt.AdtError):
+        adt.CreateHighCutFilter(4000)
+    with pytest.raises(adt.AdtError):
+        adt.CreateEQ3Band(100, 2, 700, -4, 8000, 5)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "pyaudiodsptools_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(import|from)\s+oracle\b", src, re.M), fn
