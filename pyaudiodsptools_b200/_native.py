@@ -145,7 +145,6 @@ class Context:
         self.check(self.lib.adt_malloc_host(self.h, max(n, 1), C.byref(p)))
         buf = (C.c_byte * max(n, 1)).from_address(p.value)
         arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-        _PINNED[p.value] = (self, buf)
         import weakref
         weakref.finalize(buf, _free_pinned, self.lib, self.h, p.value)
         return arr
@@ -179,11 +178,7 @@ class Context:
         return Event(self)
 
 
-_PINNED = {}
-
-
 def _free_pinned(lib, ctx_h, p):
-    _PINNED.pop(p, None)
     try:
         lib.adt_free_host(ctx_h, p)
     except Exception:
