@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -94,12 +95,15 @@ FirVariant make_variant() {
     return v;
 }
 
-const FirVariant* find_variant(int n) {
+// occ: resident CTAs per SM the variant is compiled for (register cap via __launch_bounds__)
+const FirVariant* find_variant(int n, int occ = 0) {
     static const FirVariant table[] = {
         make_variant<FirCfg<16, 8>, 4>(),   // N = 4096,  128 threads
-        make_variant<FirCfg<16, 16>, 2>(),  // N = 8192,  256 threads
+        make_variant<FirCfg<16, 16>, 2>(),  // N = 8192,  256 threads, 128 regs
         make_variant<FirCfg<16, 32>, 1>(),  // N = 16384, 512 threads
     };
+    static const FirVariant occ3 = make_variant<FirCfg<16, 16>, 3>();  // N = 8192 at 80 regs, 3 CTAs/SM
+    if (n == 8192 && occ == 3) return &occ3;
     for (const FirVariant& v : table)
         if (v.n == n) return &v;
     return nullptr;
@@ -133,10 +137,11 @@ extern "C" int adt_ctx_create(int device, adt_ctx** out) {
         delete ctx;
         return ADT_ERR_CUDA;
     }
-    for (int nfft : {4096, 8192, 16384}) {
-        const FirVariant* v = find_variant(nfft);
+    for (int nfft : {4096, 8192, 16384, -8192}) {
+        const FirVariant* v = nfft > 0 ? find_variant(nfft) : find_variant(-nfft, 3);
         for (fir_kernel_fn f : {v->cplx, v->real}) {
-            e = cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->smem);
+            e = cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(v->smem + (getenv("ADT_FIR_EXTRA_SMEM") ? atoi(getenv("ADT_FIR_EXTRA_SMEM")) : 0)));
             if (e != cudaSuccess) {
                 delete ctx;
                 return ADT_ERR_CUDA;
@@ -325,7 +330,8 @@ static int fir_launch(adt_fir* f, cudaStream_t s, const float* x, int64_t in_pit
     a.g.out_pitch = out_pitch;
     const dim3 grid((unsigned)blocks, (unsigned)pairs);
     fir_kernel_fn k = f->d.mask_is_real ? f->var->real : f->var->cplx;
-    k<<<grid, f->var->threads, f->var->smem, s>>>(a);
+    static const size_t extra_smem = getenv("ADT_FIR_EXTRA_SMEM") ? (size_t)atoi(getenv("ADT_FIR_EXTRA_SMEM")) : 0;  // occupancy experiments
+    k<<<grid, f->var->threads, f->var->smem + extra_smem, s>>>(a);
     CK(ctx, cudaGetLastError());
     ctx->launches++;
     return ADT_OK;
@@ -352,7 +358,8 @@ extern "C" int adt_fir_destroy(adt_fir* f) {
 extern "C" int adt_fir_create(adt_ctx* ctx, const adt_fir_desc* desc, const float* mask, adt_fir** out) {
     if (!ctx || !desc || !mask || !out) return ADT_ERR_INVALID;
     *out = nullptr;
-    const FirVariant* var = find_variant(desc->fft_size);
+    const char* occ_env = getenv("ADT_FIR_OCC");  // tuning knob: "3" selects the 80-register build of N = 8192
+    const FirVariant* var = find_variant(desc->fft_size, occ_env ? atoi(occ_env) : 0);
     if (!var)
         return adt_set_error(ctx, ADT_ERR_UNSUPPORTED, "fft_size %d not in {4096, 8192, 16384}", desc->fft_size);
     if (desc->hop < 1 || desc->n0 < 0 || desc->back < 0 || (int64_t)desc->n0 + desc->hop > desc->fft_size)

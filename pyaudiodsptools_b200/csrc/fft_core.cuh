@@ -17,14 +17,18 @@
 //            times W_N^(r*k1)                      -> A[k1][r]
 //   stage 2 (thread (k1, r2=lane), B2=32/N2):  DFT_N2 over n2 of A[k1][n2*32+r2],
 //            times W_M1^(r2*k2)                    -> B[k1][k2][r2]
-//   stage 3 (thread t = k1*N2 + k2):           DFT_32 over r2
+//   stage 3 (thread = (k1, k2), one row of the tile): DFT_32 over r2
 //            -> X[k1 + N1*k2 + T*k3]   (natural order, stride T across k3)
+//            Rows are assigned so that warp w owns exactly the rows its own
+//            stage-2 butterflies wrote (k1 in {w, w+WARPS, ..}): the exchanges
+//            around stage 3 are warp-local and need only __syncwarp().
 //   mask multiply in registers, then the mirror image (DIT, conjugate
 //   twiddles applied on input) back to y[n1*M1 + r].
 //
 // Shared memory holds one [T rows][33] float2 tile; every exchange is done
 // IN PLACE (each thread writes exactly the addresses it read last), so only
-// the four read-after-write barriers per block are needed.  Row pitch 33
+// read-after-write synchronisation is needed: two block barriers (around the
+// stage-1 transposition) and two warp barriers (around stage 3).  Row pitch 33
 // makes both the row-wise (stage 3) and column-wise (stages 1,2) accesses
 // bank-conflict free with immediate offsets.
 //
@@ -45,15 +49,58 @@
 
 namespace adt {
 
+// A complex number is a (re, im) pair in an aligned 64-bit register pair.  On
+// sm_100a the arithmetic below is PACKED: FADD2 / FMUL2 / FFMA2 (add/mul/fma
+// .f32x2) do both halves in one issue slot, and ptxas folds the half swaps,
+// scalar broadcasts and per-half sign flips written here with make pairs into
+// operand modifiers (.LO_HI, .F32, .NP), so e.g. a complex multiply is 2
+// instructions and a radix-2 butterfly with a general twiddle is 3 (8 scalar).
+// The host versions are the same formulas in scalar float (CPU emulation check).
+#if defined(__CUDACC__)
+typedef float2 cf;
+#else
 struct ADT_ALIGN8 cf {
     float x, y;
 };
+#endif
 
-ADT_HD cf cmul(cf a, cf b) { return cf{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
-// a * conj(b)
-ADT_HD cf cmulc(cf a, cf b) { return cf{a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y}; }
+ADT_HD cf mk(float x, float y) {
+    cf r;
+    r.x = x;
+    r.y = y;
+    return r;
+}
+ADT_HD cf cadd(cf a, cf b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd2_rn(a, b);
+#else
+    return mk(a.x + b.x, a.y + b.y);
+#endif
+}
+ADT_HD cf csub(cf a, cf b) { return cadd(a, mk(-b.x, -b.y)); }
+// acc + s * w   (s real scalar, broadcast)
+ADT_HD cf fma_s(float s, cf w, cf acc) {
+#if defined(__CUDA_ARCH__)
+    return __ffma2_rn(mk(s, s), w, acc);
+#else
+    return mk(s * w.x + acc.x, s * w.y + acc.y);
+#endif
+}
+ADT_HD cf mul_s(float s, cf w) {
+#if defined(__CUDA_ARCH__)
+    return __fmul2_rn(mk(s, s), w);
+#else
+    return mk(s * w.x, s * w.y);
+#endif
+}
+// a*b = a.x*(b.x, b.y) + a.y*(-b.y, b.x)
+ADT_HD cf cmul(cf a, cf b) { return fma_s(a.x, b, mul_s(a.y, mk(-b.y, b.x))); }
+// a * conj(b) = a.x*(b.x, -b.y) + a.y*(b.y, b.x)
+ADT_HD cf cmulc(cf a, cf b) { return fma_s(a.x, mk(b.x, -b.y), mul_s(a.y, mk(b.y, b.x))); }
+// acc + a*b
+ADT_HD cf cfma(cf a, cf b, cf acc) { return fma_s(a.x, b, fma_s(a.y, mk(-b.y, b.x), acc)); }
 
-ADT_HD cf mask_mul(cf a, float h) { return cf{a.x * h, a.y * h}; }  // zero-phase (real) mask
+ADT_HD cf mask_mul(cf a, float h) { return mul_s(h, a); }  // zero-phase (real) mask
 ADT_HD cf mask_mul(cf a, cf h) { return cmul(a, h); }
 
 // cos / sin of 2*pi*q/32 as literals (constexpr trig is not available).
@@ -90,43 +137,25 @@ ADT_HD constexpr int brev(int i) {
 
 // DIT butterfly  a' = a + W b,  b' = a - W b,  W = exp(DIR * 2*pi*i * Q/32).
 // DIR = -1: forward transform, +1: inverse.  Q in [0, 16).
+// General twiddle: a' = a + wr*b + wi*(i b) (2 FFMA2), b' = 2a - a' (1 FFMA2).
 template <int Q, int DIR>
 ADT_HD void bfly(cf& a, cf& b) {
     if constexpr (Q == 0) {
         const cf t = b;
-        b = cf{a.x - t.x, a.y - t.y};
-        a = cf{a.x + t.x, a.y + t.y};
+        b = csub(a, t);
+        a = cadd(a, t);
     } else if constexpr (Q == 8) {
         // W = i*DIR :  W b = (-DIR*b.y, DIR*b.x)
-        const cf t = b;
-        if constexpr (DIR < 0) {
-            b = cf{a.x - t.y, a.y + t.x};
-            a = cf{a.x + t.y, a.y - t.x};
-        } else {
-            b = cf{a.x + t.y, a.y - t.x};
-            a = cf{a.x - t.y, a.y + t.x};
-        }
-    } else if constexpr (Q == 4) {
-        // W = c*(1 + i*DIR):  W b = c*(b.x - DIR*b.y, b.y + DIR*b.x)
-        constexpr float c = 0.70710678118654752f;
-        const float s = (DIR < 0) ? (b.x + b.y) : (b.x - b.y);
-        const float d = (DIR < 0) ? (b.y - b.x) : (b.y + b.x);
-        b = cf{a.x - c * s, a.y - c * d};
-        a = cf{a.x + c * s, a.y + c * d};
-    } else if constexpr (Q == 12) {
-        // W = c*(-1 + i*DIR): W b = c*(-b.x - DIR*b.y, -b.y + DIR*b.x)
-        constexpr float c = 0.70710678118654752f;
-        const float s = (DIR < 0) ? (b.y - b.x) : (-b.x - b.y);
-        const float d = (DIR < 0) ? (-b.y - b.x) : (b.x - b.y);
-        b = cf{a.x - c * s, a.y - c * d};
-        a = cf{a.x + c * s, a.y + c * d};
+        const cf t = (DIR < 0) ? mk(b.y, -b.x) : mk(-b.y, b.x);
+        b = csub(a, t);
+        a = cadd(a, t);
     } else {
         constexpr float wr = cos32(Q);
         constexpr float wi = (DIR < 0) ? -sin32(Q) : sin32(Q);
-        const float tr = wr * b.x - wi * b.y;
-        const float ti = wr * b.y + wi * b.x;
-        b = cf{a.x - tr, a.y - ti};
-        a = cf{a.x + tr, a.y + ti};
+        // W b = wr*(b.x, b.y) + wi*(-b.y, b.x): constants as broadcast immediates, data swizzled
+        const cf a1 = fma_s(wr, b, fma_s(wi, mk(-b.y, b.x), a));
+        b = fma_s(2.0f, a, mk(-a1.x, -a1.y));
+        a = a1;
     }
 }
 
@@ -173,25 +202,38 @@ ADT_HD constexpr int hibit(int k) {  // largest power of two <= k
     return h;
 }
 
-// Powers w^1..w^(R-1) of a unit-modulus base by a depth-log2(R) product tree
-// (w^k from w^(k - p) * w^p with p the highest power of two below k ... ),
-// then multiply v[brev(k)] by them.  CONJ selects conj(w^k).
-template <int R, bool CONJ>
+// Multiply element k (k = 1..R-1) by w^k (or conj(w^k)) for a unit-modulus base w.
+// Powers come from a small basis kept in registers — b[j] = w^j (j = 1..3) and
+// q[a] = w^(4a) — and every other power is the just-in-time product q[a]*b[j],
+// so only R/4 + 2 pairs are live instead of R - 1 (matters at 80 registers).
+// Product-tree depth is <= log2(R) + 1, i.e. a few ulp of error on the twiddle.
+// BREV: element k lives at v[brev<R>(k)] (output of dft<>) instead of v[k].
+template <int R, bool CONJ, bool BREV>
 ADT_HD void apply_powers(cf* v, cf w1) {
-    cf p[R];
-    p[1] = w1;
-    static_for<2, R>([&](auto K) {
-        constexpr int k = decltype(K)::value;
-        constexpr int hi = (k & (k - 1)) == 0 ? k / 2 : hibit(k);
-        constexpr int lo = k - hi;
-        p[k] = cmul(p[hi], p[lo]);
+    static_assert(R >= 8 && R % 4 == 0, "radix");
+    constexpr int A = R / 4;
+    cf b[4], q[A];
+    b[1] = w1;
+    b[2] = cmul(w1, w1);
+    b[3] = cmul(b[2], w1);
+    q[1] = cmul(b[2], b[2]);
+    static_for<2, A>([&](auto K) {
+        constexpr int a = decltype(K)::value;
+        constexpr int hi = (a & (a - 1)) == 0 ? a / 2 : hibit(a);
+        q[a] = cmul(q[hi], q[a - hi]);
     });
     static_for<1, R>([&](auto K) {
         constexpr int k = decltype(K)::value;
-        if constexpr (CONJ)
-            v[k] = cmulc(v[k], p[k]);
+        constexpr int a = k / 4, j = k % 4;
+        constexpr int idx = BREV ? brev<R>(k) : k;
+        cf p;
+        if constexpr (a == 0)
+            p = b[j];
+        else if constexpr (j == 0)
+            p = q[a];
         else
-            v[brev<R>(k)] = cmul(v[brev<R>(k)], p[k]);
+            p = cmul(q[a], b[j]);
+        v[idx] = CONJ ? cmulc(v[idx], p) : cmul(v[idx], p);
     });
 }
 
@@ -209,6 +251,10 @@ struct FirCfg {
     static constexpr int PITCH = 33;         // float2 per tile row
     static constexpr int TILE = T * PITCH;   // float2 elements of shared memory
     static constexpr int WARPS = T / 32;
+    // tile row (k1*N2 + k2) owned by thread t in stage 3: the rows written by t's own warp in stage 2
+    ADT_HD static constexpr int stage3_row(int t) {
+        return (((t >> 5) + ((t & 31) / N2) * WARPS) * N2) + ((t & 31) % N2);
+    }
 };
 
 // What one FIR block needs to know (see DESIGN.md §3 for the derivation).
@@ -232,7 +278,7 @@ ADT_HD void load_window(cf* v, int t, const float* __restrict__ xa, const float*
             static_for<0, C::N1>([&](auto K) {
                 constexpr int u = decltype(U)::value, n1 = decltype(K)::value;
                 const long long s = ws + n1 * C::M1 + t + u * C::T;
-                v[u * C::N1 + n1] = cf{xa[s], xb ? xb[s] : 0.0f};
+                v[u * C::N1 + n1] = mk(xa[s], xb ? xb[s] : 0.0f);
             });
         });
     } else {
@@ -241,7 +287,7 @@ ADT_HD void load_window(cf* v, int t, const float* __restrict__ xa, const float*
                 constexpr int u = decltype(U)::value, n1 = decltype(K)::value;
                 const long long s = ws + n1 * C::M1 + t + u * C::T;
                 const bool ok = (s >= 0) && (s < n_in);
-                v[u * C::N1 + n1] = cf{ok ? xa[s] : 0.0f, (ok && xb) ? xb[s] : 0.0f};
+                v[u * C::N1 + n1] = mk(ok ? xa[s] : 0.0f, (ok && xb) ? xb[s] : 0.0f);
             });
         });
     }
@@ -256,7 +302,7 @@ ADT_HD void fwd_stage1(cf* v, int t, const cf* __restrict__ tw1, cf* tile) {
         cf* b = v + u * C::N1;
         dft<C::N1, -1>(b);
         const int r = t + u * C::T;
-        apply_powers<C::N1, false>(b, tw1[r]);
+        apply_powers<C::N1, false, true>(b, tw1[r]);
         const int row0 = r >> 5;  // n2
         static_for<0, C::N1>([&](auto K) {
             constexpr int k1 = decltype(K)::value;
@@ -269,17 +315,17 @@ ADT_HD void fwd_stage1(cf* v, int t, const cf* __restrict__ tw1, cf* tile) {
 template <class C>
 ADT_HD void fwd_stage2(cf* v, int t, const cf* __restrict__ tw2, cf* tile) {
     const int lane = t & 31, warp = t >> 5;
+    const cf w2 = tw2[lane];  // W_M1^lane; the stage-2 twiddles are its powers W_M1^(lane*k2)
     static_for<0, C::B2>([&](auto U) {
         constexpr int u = decltype(U)::value;
         cf* b = v + u * C::N2;
         cf* col = tile + ((warp + u * C::WARPS) * C::N2) * C::PITCH + lane;
         static_for<0, C::N2>([&](auto K) { constexpr int n2 = decltype(K)::value; b[n2] = col[n2 * C::PITCH]; });
         dft<C::N2, -1>(b);
+        apply_powers<C::N2, false, true>(b, w2);
         static_for<0, C::N2>([&](auto K) {
             constexpr int k2 = decltype(K)::value;
-            cf val = b[brev<C::N2>(k2)];
-            if constexpr (k2 > 0) val = cmul(val, tw2[k2 * 32 + lane]);
-            col[k2 * C::PITCH] = val;
+            col[k2 * C::PITCH] = b[brev<C::N2>(k2)];
         });
     });
 }
@@ -287,7 +333,7 @@ ADT_HD void fwd_stage2(cf* v, int t, const cf* __restrict__ tw2, cf* tile) {
 // ---- phase 3: forward DFT32, mask, inverse DFT32, in place row t ------------
 template <class C, class MaskT>
 ADT_HD void mid_stage3(cf* v, int t, const MaskT* __restrict__ mask, cf* tile) {
-    cf* row = tile + t * C::PITCH;
+    cf* row = tile + C::stage3_row(t) * C::PITCH;
     static_for<0, 32>([&](auto K) { constexpr int r2 = decltype(K)::value; v[r2] = row[r2]; });
     dft<32, -1>(v);
     cf y[32];
@@ -304,16 +350,13 @@ ADT_HD void mid_stage3(cf* v, int t, const MaskT* __restrict__ mask, cf* tile) {
 template <class C>
 ADT_HD void inv_stage2(cf* v, int t, const cf* __restrict__ tw2, cf* tile) {
     const int lane = t & 31, warp = t >> 5;
+    const cf w2 = tw2[lane];
     static_for<0, C::B2>([&](auto U) {
         constexpr int u = decltype(U)::value;
         cf* b = v + u * C::N2;
         cf* col = tile + ((warp + u * C::WARPS) * C::N2) * C::PITCH + lane;
-        static_for<0, C::N2>([&](auto K) {
-            constexpr int k2 = decltype(K)::value;
-            cf val = col[k2 * C::PITCH];
-            if constexpr (k2 > 0) val = cmulc(val, tw2[k2 * 32 + lane]);
-            b[k2] = val;
-        });
+        static_for<0, C::N2>([&](auto K) { constexpr int k2 = decltype(K)::value; b[k2] = col[k2 * C::PITCH]; });
+        apply_powers<C::N2, true, false>(b, w2);
         dft<C::N2, +1>(b);
         static_for<0, C::N2>([&](auto K) { constexpr int n2 = decltype(K)::value; col[n2 * C::PITCH] = b[brev<C::N2>(n2)]; });
     });
@@ -333,7 +376,7 @@ ADT_HD void inv_stage1(cf* v, int t, const cf* __restrict__ tw1, const cf* tile)
             constexpr int k1 = decltype(K)::value;
             b[k1] = tile[(k1 * C::N2 + row0) * C::PITCH + lane];
         });
-        apply_powers<C::N1, true>(b, tw1[r]);
+        apply_powers<C::N1, true, false>(b, tw1[r]);
         dft<C::N1, +1>(b);
     });
 }

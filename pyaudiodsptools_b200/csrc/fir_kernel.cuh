@@ -17,7 +17,7 @@ struct FirKernelArgs {
     float* y;              // [n_rows][out_pitch]
     const void* mask;      // kernel-order mask (float or float2 per bin), 1/N folded in
     const cf* tw1;         // [M1]
-    const cf* tw2;         // [N2*32]
+    const cf* tw2;         // [32]
     int n_rows;            // channels
     FirGeom g;
 };
@@ -44,9 +44,9 @@ __global__ void __launch_bounds__(C::T, MIN_CTAS) fir_block_kernel(const FirKern
     fwd_stage1<C>(v, t, a.tw1, tile);
     __syncthreads();
     fwd_stage2<C>(v, t, a.tw2, tile);
-    __syncthreads();
+    __syncwarp();  // stage 3 reads only rows written by this warp
     mid_stage3<C, MaskT>(v, t, reinterpret_cast<const MaskT*>(a.mask), tile);
-    __syncthreads();
+    __syncwarp();
     inv_stage2<C>(v, t, a.tw2, tile);
     __syncthreads();
     inv_stage1<C>(v, t, a.tw1, tile);

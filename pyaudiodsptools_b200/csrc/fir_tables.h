@@ -15,27 +15,27 @@ inline std::vector<cf> build_tw1() {
     std::vector<cf> tw(C::M1);
     for (int r = 0; r < C::M1; ++r) {
         const double a = -2.0 * M_PI * (double)r / (double)C::N;
-        tw[r] = cf{(float)std::cos(a), (float)std::sin(a)};
+        tw[r] = mk((float)std::cos(a), (float)std::sin(a));
     }
     return tw;
 }
 
-// tw2[k2*32 + lane] = exp(-2*pi*i * lane*k2 / M1)
+// tw2[lane] = exp(-2*pi*i * lane / M1): base of the stage-2 twiddles W_M1^(lane*k2)
 template <class C>
 inline std::vector<cf> build_tw2() {
-    std::vector<cf> tw(C::N2 * 32);
-    for (int k2 = 0; k2 < C::N2; ++k2)
-        for (int lane = 0; lane < 32; ++lane) {
-            const double a = -2.0 * M_PI * (double)(lane * k2) / (double)C::M1;
-            tw[k2 * 32 + lane] = cf{(float)std::cos(a), (float)std::sin(a)};
-        }
+    std::vector<cf> tw(32);
+    for (int lane = 0; lane < 32; ++lane) {
+        const double a = -2.0 * M_PI * (double)lane / (double)C::M1;
+        tw[lane] = mk((float)std::cos(a), (float)std::sin(a));
+    }
     return tw;
 }
 
 // Frequency index held by thread t at register k3 after forward stage 3.
 template <class C>
 inline int freq_index(int t, int k3) {
-    const int k1 = t / C::N2, k2 = t % C::N2;
+    const int row = C::stage3_row(t);
+    const int k1 = row / C::N2, k2 = row % C::N2;
     return k1 + C::N1 * k2 + C::T * k3;
 }
 

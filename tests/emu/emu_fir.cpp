@@ -56,7 +56,7 @@ extern "C" int emu_fir_block(int n, const float* xa, const float* xb, long long 
 // plain R-point DFT through the register template, for unit-testing dft<R,DIR>
 extern "C" int emu_dft(int r, int dir, float* v /* 2*r floats in/out, natural order */) {
     cf a[32], b[32];
-    for (int i = 0; i < r; ++i) a[i] = cf{v[2 * i], v[2 * i + 1]};
+    for (int i = 0; i < r; ++i) a[i] = mk(v[2 * i], v[2 * i + 1]);
 #define D(R)                                                   \
     if (r == R) {                                              \
         if (dir < 0) dft<R, -1>(a); else dft<R, +1>(a);        \

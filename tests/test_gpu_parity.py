@@ -100,7 +100,7 @@ def test_first_calls_and_latency(gpu_lib):
     dev = adt.CreateHighCutFilter(4000)
     x = np.zeros(512, dtype=np.float32); x[0] = 1.0
     y0 = dev.apply(x)
-    assert not y0[: 512 - 127].any() and y0[512 - 127:].any()
+    assert np.max(np.abs(y0[: 512 - 127])) < 1e-6 and np.max(np.abs(y0[512 - 127:])) > 1e-4   # FFT rounding noise only
     y1 = dev.apply(np.zeros(512, dtype=np.float32))
     taps = oracle.highcut_taps(44100, 512, 4000)
     full = np.concatenate([y0, y1])
