@@ -72,40 +72,76 @@ namespace {
 
 typedef void (*fir_kernel_fn)(const FirKernelArgs);
 
+struct HostTables {
+    std::vector<cf> tw1, tw2;
+    std::vector<float> coef_s, coef_x;  // kernel-order mask (and, 16-point variant, the cross coefficients)
+};
+
 struct FirVariant {
+    const char* name;
     int n, threads;
     size_t smem;
     fir_kernel_fn cplx, real;
-    std::vector<cf> (*tw1)();
-    std::vector<cf> (*tw2)();
-    std::vector<float> (*permute)(const float*, bool);
+    void (*build)(const float* mask, bool real_only, HostTables& out);
 };
 
+// 32 points per thread (fft_core.cuh)
 template <class C, int MIN_CTAS>
-FirVariant make_variant() {
+FirVariant make_variant32(const char* name) {
     FirVariant v;
+    v.name = name;
     v.n = C::N;
     v.threads = C::T;
-    v.smem = fir_smem_bytes<C>();
+    v.smem = (size_t)C::TILE * sizeof(cf);
     v.cplx = fir_block_kernel<C, cf, MIN_CTAS>;
     v.real = fir_block_kernel<C, float, MIN_CTAS>;
-    v.tw1 = build_tw1<C>;
-    v.tw2 = build_tw2<C>;
-    v.permute = permute_mask<C>;
+    v.build = [](const float* mask, bool real_only, HostTables& out) {
+        out.tw1 = build_tw1<C>();
+        out.tw2 = build_tw2<C>();
+        out.coef_s = permute_mask<C>(mask, real_only);
+        out.coef_x.clear();
+    };
+    return v;
+}
+// 16 points per thread (fft_core16.cuh)
+template <class C, int MIN_CTAS>
+FirVariant make_variant16(const char* name) {
+    FirVariant v;
+    v.name = name;
+    v.n = C::N;
+    v.threads = C::T;
+    v.smem = (size_t)C::TILE * sizeof(cf);
+    v.cplx = fir16_block_kernel<C, cf, MIN_CTAS>;
+    v.real = fir16_block_kernel<C, float, MIN_CTAS>;
+    v.build = [](const float* mask, bool real_only, HostTables& out) {
+        out.tw1 = build16_tw1<C>();
+        out.tw2 = build16_tw2<C>();
+        build16_coef<C>(mask, real_only, out.coef_s, out.coef_x);
+    };
     return v;
 }
 
-// occ: resident CTAs per SM the variant is compiled for (register cap via __launch_bounds__)
-const FirVariant* find_variant(int n, int occ = 0) {
+const FirVariant* all_variants(int* count) {
     static const FirVariant table[] = {
-        make_variant<FirCfg<16, 8>, 4>(),   // N = 4096,  128 threads
-        make_variant<FirCfg<16, 16>, 2>(),  // N = 8192,  256 threads, 128 regs
-        make_variant<FirCfg<16, 32>, 1>(),  // N = 16384, 512 threads
+        // default per size first; ADT_FIR_KERNEL=<name> overrides (A/B experiments)
+        make_variant16<Fir16Cfg<16>, 4>("p16"),    // N = 4096,  256 threads, <= 64 regs
+        make_variant16<Fir16Cfg<32>, 2>("p16"),    // N = 8192,  512 threads, <= 64 regs, 32 warps/SM
+        make_variant32<FirCfg<16, 32>, 1>("p32"),  // N = 16384, 512 threads, 128 regs
+        make_variant32<FirCfg<16, 8>, 4>("p32"),   // N = 4096,  128 threads
+        make_variant32<FirCfg<16, 16>, 2>("p32"),  // N = 8192,  256 threads, 128 regs
     };
-    static const FirVariant occ3 = make_variant<FirCfg<16, 16>, 3>();  // N = 8192 at 80 regs, 3 CTAs/SM
-    if (n == 8192 && occ == 3) return &occ3;
-    for (const FirVariant& v : table)
-        if (v.n == n) return &v;
+    *count = (int)(sizeof table / sizeof table[0]);
+    return table;
+}
+
+const FirVariant* find_variant(int n, const char* name = nullptr) {
+    int cnt = 0;
+    const FirVariant* t = all_variants(&cnt);
+    if (name && *name)
+        for (int i = 0; i < cnt; ++i)
+            if (t[i].n == n && !strcmp(t[i].name, name)) return &t[i];
+    for (int i = 0; i < cnt; ++i)
+        if (t[i].n == n) return &t[i];
     return nullptr;
 }
 
@@ -137,8 +173,10 @@ extern "C" int adt_ctx_create(int device, adt_ctx** out) {
         delete ctx;
         return ADT_ERR_CUDA;
     }
-    for (int nfft : {4096, 8192, 16384, -8192}) {
-        const FirVariant* v = nfft > 0 ? find_variant(nfft) : find_variant(-nfft, 3);
+    int n_var = 0;
+    const FirVariant* vars = all_variants(&n_var);
+    for (int vi = 0; vi < n_var; ++vi) {
+        const FirVariant* v = &vars[vi];
         for (fir_kernel_fn f : {v->cplx, v->real}) {
             e = cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)(v->smem + (getenv("ADT_FIR_EXTRA_SMEM") ? atoi(getenv("ADT_FIR_EXTRA_SMEM")) : 0)));
@@ -290,9 +328,11 @@ struct adt_fir {
     adt_fir_desc d{};
     const FirVariant* var = nullptr;
     void* d_mask = nullptr;
+    cf* d_coef_x = nullptr;
     cf* d_tw1 = nullptr;
     cf* d_tw2 = nullptr;
     // streaming state: two [n_channels][hist_pitch] buffers (history ++ newest chunk)
+    int resident_ctas = 0;  // CTAs resident at once (SMs x CTAs per SM), computed on first launch
     float* d_hist[2] = {nullptr, nullptr};
     int cur = 0;
     int64_t hist_pitch = 0;
@@ -310,16 +350,18 @@ static int fir_launch(adt_fir* f, cudaStream_t s, const float* x, int64_t in_pit
     if (n_rows <= 0 || n_out <= 0) return ADT_OK;
     const int64_t blocks = (n_out + f->d.hop - 1) / f->d.hop;
     const int64_t pairs = (n_rows + 1) / 2;
-    if (blocks > 0x7fffffffLL || pairs > 65535)
-        return adt_set_error(ctx, ADT_ERR_UNSUPPORTED, "grid too large: %lld blocks x %lld channel pairs",
-                             (long long)blocks, (long long)pairs);
+    if (blocks > 0x7fffffffLL)
+        return adt_set_error(ctx, ADT_ERR_UNSUPPORTED, "too many blocks per row: %lld", (long long)blocks);
     FirKernelArgs a;
     a.x = x;
     a.y = y;
     a.mask = f->d_mask;
+    a.coef_x = f->d_coef_x;
     a.tw1 = f->d_tw1;
     a.tw2 = f->d_tw2;
     a.n_rows = n_rows;
+    a.blocks_per_row = (int)blocks;
+    a.n_items = blocks * pairs;
     a.g.hop = f->d.hop;
     a.g.n0 = f->d.n0;
     a.g.back = f->d.back;
@@ -328,8 +370,19 @@ static int fir_launch(adt_fir* f, cudaStream_t s, const float* x, int64_t in_pit
     a.g.n_out = n_out;
     a.g.in_pitch = in_pitch;
     a.g.out_pitch = out_pitch;
-    const dim3 grid((unsigned)blocks, (unsigned)pairs);
     fir_kernel_fn k = f->d.mask_is_real ? f->var->real : f->var->cplx;
+    if (a.n_items > 0x7fffffffLL)
+        return adt_set_error(ctx, ADT_ERR_UNSUPPORTED, "too many work items: %lld", (long long)a.n_items);
+    if (f->resident_ctas == 0) {  // CTAs in flight at once = how far ahead the L2 prefetch looks
+        int per_sm = 0, sms = 0;
+        CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, f->var->threads, f->var->smem));
+        CK(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+        f->resident_ctas = per_sm > 0 ? per_sm * sms : sms;
+    }
+    // L2 prefetch distance in units of one wave of resident CTAs (measured best ~0.5-1 for N >= 8192, off for 4096)
+    const double pf = getenv("ADT_FIR_PREFETCH") ? atof(getenv("ADT_FIR_PREFETCH")) : (f->d.fft_size >= 8192 ? 0.5 : 0.0);
+    a.prefetch_ahead = (int)(pf * f->resident_ctas);
+    const unsigned grid = (unsigned)a.n_items;
     static const size_t extra_smem = getenv("ADT_FIR_EXTRA_SMEM") ? (size_t)atoi(getenv("ADT_FIR_EXTRA_SMEM")) : 0;  // occupancy experiments
     k<<<grid, f->var->threads, f->var->smem + extra_smem, s>>>(a);
     CK(ctx, cudaGetLastError());
@@ -342,6 +395,7 @@ extern "C" int adt_fir_destroy(adt_fir* f) {
     cudaSetDevice(f->ctx->device);
     cudaDeviceSynchronize();
     cudaFree(f->d_mask);
+    cudaFree(f->d_coef_x);
     cudaFree(f->d_tw1);
     cudaFree(f->d_tw2);
     cudaFree(f->d_hist[0]);
@@ -358,8 +412,11 @@ extern "C" int adt_fir_destroy(adt_fir* f) {
 extern "C" int adt_fir_create(adt_ctx* ctx, const adt_fir_desc* desc, const float* mask, adt_fir** out) {
     if (!ctx || !desc || !mask || !out) return ADT_ERR_INVALID;
     *out = nullptr;
-    const char* occ_env = getenv("ADT_FIR_OCC");  // tuning knob: "3" selects the 80-register build of N = 8192
-    const FirVariant* var = find_variant(desc->fft_size, occ_env ? atoi(occ_env) : 0);
+    // Default kernel family (measured): "p32" (32 points/thread) everywhere except N = 4096
+    // with a real mask, where "p16" (16 points/thread) is marginally faster.  ADT_FIR_KERNEL overrides (A/B).
+    const char* want = getenv("ADT_FIR_KERNEL");
+    if (!want || !*want) want = (desc->fft_size == 4096 && desc->mask_is_real) ? "p16" : "p32";
+    const FirVariant* var = find_variant(desc->fft_size, want);
     if (!var)
         return adt_set_error(ctx, ADT_ERR_UNSUPPORTED, "fft_size %d not in {4096, 8192, 16384}", desc->fft_size);
     if (desc->hop < 1 || desc->n0 < 0 || desc->back < 0 || (int64_t)desc->n0 + desc->hop > desc->fft_size)
@@ -373,12 +430,17 @@ extern "C" int adt_fir_create(adt_ctx* ctx, const adt_fir_desc* desc, const floa
     f->ctx = ctx;
     f->d = *desc;
     f->var = var;
-    const std::vector<cf> tw1 = var->tw1(), tw2 = var->tw2();
-    const std::vector<float> pm = var->permute(mask, desc->mask_is_real != 0);
-    cudaError_t e = cudaMalloc(&f->d_mask, pm.size() * sizeof(float));
+    HostTables ht;
+    var->build(mask, desc->mask_is_real != 0, ht);
+    const std::vector<cf>&tw1 = ht.tw1, &tw2 = ht.tw2;
+    cudaError_t e = cudaMalloc(&f->d_mask, ht.coef_s.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_tw1, tw1.size() * sizeof(cf));
     if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_tw2, tw2.size() * sizeof(cf));
-    if (e == cudaSuccess) e = cudaMemcpy(f->d_mask, pm.data(), pm.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_coef_x, ht.coef_x.size() * sizeof(float) + 8);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(f->d_mask, ht.coef_s.data(), ht.coef_s.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !ht.coef_x.empty())
+        e = cudaMemcpy(f->d_coef_x, ht.coef_x.data(), ht.coef_x.size() * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(f->d_tw1, tw1.data(), tw1.size() * sizeof(cf), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(f->d_tw2, tw2.data(), tw2.size() * sizeof(cf), cudaMemcpyHostToDevice);
     if (e == cudaSuccess && desc->n_channels > 0) {

@@ -61,4 +61,60 @@ inline std::vector<float> permute_mask(const float* mask_natural, bool real_only
     return out;
 }
 
+// ---- 16-points-per-thread variant (fft_core16.cuh) ---------------------------
+template <class C>
+inline std::vector<cf> build16_tw1() {
+    std::vector<cf> tw(C::M1);
+    for (int r = 0; r < C::M1; ++r) {
+        const double a = -2.0 * M_PI * (double)r / (double)C::N;
+        tw[r] = mk((float)std::cos(a), (float)std::sin(a));
+    }
+    return tw;
+}
+template <class C>
+inline std::vector<cf> build16_tw2() {
+    std::vector<cf> tw(C::N3);
+    for (int r2 = 0; r2 < C::N3; ++r2) {
+        const double a = -2.0 * M_PI * (double)r2 / (double)C::M1;
+        tw[r2] = mk((float)std::cos(a), (float)std::sin(a));
+    }
+    return tw;
+}
+// Stage-3 coefficients.  Complex mask: coefS[j*T + t] (float2), coefX[j*T + t] (float2) per thread.
+// Real mask with N3 = 32: both lanes of a row share coefS[j*256 + row] (float) and
+// coefX[j*256 + row] = Hd*W32^j (float2; lane B conjugates it).  N3 = 16: coefS only, per thread.
+template <class C>
+inline void build16_coef(const float* mask_natural, bool real_only, std::vector<float>& coef_s,
+                         std::vector<float>& coef_x) {
+    const double inv = 1.0 / (double)C::N;
+    const bool shared_rows = real_only && C::N3 == 32;
+    const int cols = shared_rows ? 256 : C::T;
+    coef_s.assign((size_t)16 * cols * (real_only ? 1 : 2), 0.f);
+    coef_x.assign(C::N3 == 32 ? (size_t)16 * cols * 2 : 0, 0.f);
+    for (int j = 0; j < 16; ++j)
+        for (int c = 0; c < cols; ++c) {
+            const int row = shared_rows ? c : C::s3_row(c), half = shared_rows ? 0 : C::s3_half(c);
+            const int k_lo = row / 16 + 16 * (row % 16) + 256 * j;
+            const size_t o = (size_t)j * cols + c;
+            double lr = mask_natural[2 * k_lo], li = real_only ? 0.0 : mask_natural[2 * k_lo + 1];
+            double sr = lr, si = li;
+            if (C::N3 == 32) {
+                const int k_hi = k_lo + C::N / 2;
+                const double hr = mask_natural[2 * k_hi], hi = real_only ? 0.0 : mask_natural[2 * k_hi + 1];
+                sr = lr + hr; si = li + hi;
+                const double dr = lr - hr, di = li - hi;
+                const double ang = (half ? +1.0 : -1.0) * 2.0 * M_PI * (double)j / 32.0;
+                const double wr = std::cos(ang), wi = std::sin(ang);
+                coef_x[2 * o] = (float)((dr * wr - di * wi) * inv);
+                coef_x[2 * o + 1] = (float)((dr * wi + di * wr) * inv);
+            }
+            if (real_only) {
+                coef_s[o] = (float)(sr * inv);
+            } else {
+                coef_s[2 * o] = (float)(sr * inv);
+                coef_s[2 * o + 1] = (float)(si * inv);
+            }
+        }
+}
+
 }  // namespace adt

@@ -79,19 +79,28 @@ class BlockPlan:
     delay: int
 
 
+# Measured cost of one FFT point (kernel time per transform point, relative to N = 8192) on B200,
+# gpurun_out/q7: the 4-CTA/SM N = 4096 kernels overlap memory and FP phases best, the 1-CTA/SM
+# N = 16384 kernel worst.  The planner minimises cost / (hop / N).
+_POINT_COST = {4096: 0.82, 8192: 1.00, 16384: 1.36}
+
+
 def _pick_fft_size(n_taps: int) -> int:
     forced = os.environ.get("ADT_FFT_SIZE")
     if forced:
         return int(forced)
-    # 8192 is the best-tuned kernel; fall to 16384 when it would keep < 60 % of each block
-    for n in (8192, 16384):
-        if n - (n_taps - 1) >= 0.6 * n:
-            return n
-    for n in (8192, 16384):
-        if n - (n_taps - 1) >= 32:
-            return n
-    raise ValueError(f"a {n_taps}-tap filter needs an FFT larger than {SUPPORTED_FFT[-1]} "
-                     "(chunk_size too large for this build)")
+    best = None
+    for n, cost in _POINT_COST.items():
+        hop = n - (n_taps - 1) - 32        # 32: worst-case alignment slack of plan_block
+        if hop < 32:
+            continue
+        score = cost * n / hop
+        if best is None or score < best[0]:
+            best = (score, n)
+    if best is None:
+        raise ValueError(f"a {n_taps}-tap filter needs an FFT larger than {SUPPORTED_FFT[-1]} "
+                         "(chunk_size too large for this build)")
+    return best[1]
 
 
 def plan_block(taps: np.ndarray, delay: int, fft_size: int | None = None) -> BlockPlan:

@@ -19,6 +19,7 @@ EMU_DIR = os.path.join(HERE, "emu")
 SO = os.path.join(EMU_DIR, "libemu_fir.so")
 SRC = [os.path.join(EMU_DIR, "emu_fir.cpp"),
        os.path.join(HERE, "..", "pyaudiodsptools_b200", "csrc", "fft_core.cuh"),
+       os.path.join(HERE, "..", "pyaudiodsptools_b200", "csrc", "fft_core16.cuh"),
        os.path.join(HERE, "..", "pyaudiodsptools_b200", "csrc", "fir_tables.h")]
 
 
@@ -30,6 +31,7 @@ def emu():
     fp = ctypes.POINTER(ctypes.c_float)
     lib.emu_fir_block.argtypes = [ctypes.c_int, fp, fp, ctypes.c_longlong, ctypes.c_longlong, fp, ctypes.c_int, fp]
     lib.emu_dft.argtypes = [ctypes.c_int, ctypes.c_int, fp]
+    lib.emu_fir16_block.argtypes = lib.emu_fir_block.argtypes
     return lib
 
 
@@ -49,9 +51,11 @@ def test_register_dft(emu, r, direction):
     assert np.max(np.abs(got - want)) < 2e-6 * np.sqrt(r) * np.max(np.abs(want))
 
 
-@pytest.mark.parametrize("n", [2048, 4096, 8192, 16384, 32768])
+@pytest.mark.parametrize("n,variant", [(2048, 32), (4096, 32), (8192, 32), (16384, 32), (32768, 32), (4096, 16), (8192, 16)])
 @pytest.mark.parametrize("real_mask", [0, 1])
-def test_fir_block_equals_circular_convolution(emu, n, real_mask):
+def test_fir_block_equals_circular_convolution(emu, n, variant, real_mask):
+    """variant = complex points held per thread (32: fft_core.cuh, 16: fft_core16.cuh)."""
+    run = emu.emu_fir_block if variant == 32 else emu.emu_fir16_block
     rng = np.random.default_rng(n + real_mask)
     n_in = 3 * n
     xa = rng.uniform(-1, 1, n_in).astype(np.float32)
@@ -63,7 +67,7 @@ def test_fir_block_equals_circular_convolution(emu, n, real_mask):
     Hc = np.ascontiguousarray(H.astype(np.complex64).view(np.float32))
     for ws in (n // 2 + 3, -100, n_in - n // 3):   # interior, left edge, right edge (zero fill)
         z = np.zeros(2 * n, dtype=np.float32)
-        assert emu.emu_fir_block(n, _p(xa), _p(xb), n_in, ws, _p(Hc), real_mask, _p(z)) == 0
+        assert run(n, _p(xa), _p(xb), n_in, ws, _p(Hc), real_mask, _p(z)) == 0
         idx = ws + np.arange(n)
         ok = (idx >= 0) & (idx < n_in)
         w = np.where(ok, xa[np.clip(idx, 0, n_in - 1)], 0) + 1j * np.where(ok, xb[np.clip(idx, 0, n_in - 1)], 0)

@@ -51,10 +51,12 @@ def test_whole_buffer_matches_reference(gpu_lib, name):
     assert np.max(np.abs(y - arr["y"])) <= MAX_TOL
 
 
-@pytest.mark.parametrize("fft_size", [4096, 8192, 16384])
+@pytest.mark.parametrize("fft_size,kernel", [(4096, "p16"), (8192, "p16"), (4096, "p32"), (8192, "p32"), (16384, "p32")])
 @pytest.mark.parametrize("name", ["highcut4000_c512_noise", "eq3fft_c512_noise", "lowcut160_default_c1024_noise"])
-def test_every_kernel_size(gpu_lib, name, fft_size):
+def test_every_kernel_variant(gpu_lib, monkeypatch, name, fft_size, kernel):
+    """p16 / p32 = 16 / 32 complex points per thread (fft_core16.cuh / fft_core.cuh), real and complex masks."""
     meta, arr = load_golden(name)
+    monkeypatch.setenv("ADT_FIR_KERNEL", kernel)
     dev = _make(meta, fft_size=fft_size)
     assert dev.plan.fft_size == fft_size
     y = dev.process(arr["x"])
