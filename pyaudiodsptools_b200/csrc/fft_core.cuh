@@ -208,7 +208,8 @@ ADT_HD constexpr int hibit(int k) {  // largest power of two <= k
 // so only R/4 + 2 pairs are live instead of R - 1 (matters at 80 registers).
 // Product-tree depth is <= log2(R) + 1, i.e. a few ulp of error on the twiddle.
 // BREV: element k lives at v[brev<R>(k)] (output of dft<>) instead of v[k].
-template <int R, bool CONJ, bool BREV>
+// NB butterflies stored back to back (v + u*R) share the same base: powers are formed once.
+template <int R, bool CONJ, bool BREV, int NB = 1>
 ADT_HD void apply_powers(cf* v, cf w1) {
     static_assert(R >= 8 && R % 4 == 0, "radix");
     constexpr int A = R / 4;
@@ -233,7 +234,10 @@ ADT_HD void apply_powers(cf* v, cf w1) {
             p = q[a];
         else
             p = cmul(q[a], b[j]);
-        v[idx] = CONJ ? cmulc(v[idx], p) : cmul(v[idx], p);
+        static_for<0, NB>([&](auto U) {
+            constexpr int o = decltype(U)::value * R + idx;
+            v[o] = CONJ ? cmulc(v[o], p) : cmul(v[o], p);
+        });
     });
 }
 
@@ -312,17 +316,23 @@ ADT_HD void fwd_stage1(cf* v, int t, const cf* __restrict__ tw1, cf* tile) {
 }
 
 // ---- phase 2: forward stage 2, in place in the tile --------------------------
+// The twiddle W_M1^(lane*k2) does not depend on k1, so all B2 butterflies of a thread share it.
 template <class C>
 ADT_HD void fwd_stage2(cf* v, int t, const cf* __restrict__ tw2, cf* tile) {
     const int lane = t & 31, warp = t >> 5;
-    const cf w2 = tw2[lane];  // W_M1^lane; the stage-2 twiddles are its powers W_M1^(lane*k2)
+    const cf w2 = tw2[lane];  // W_M1^lane; the stage-2 twiddles are its powers
+    static_for<0, C::B2>([&](auto U) {
+        constexpr int u = decltype(U)::value;
+        cf* b = v + u * C::N2;
+        const cf* col = tile + ((warp + u * C::WARPS) * C::N2) * C::PITCH + lane;
+        static_for<0, C::N2>([&](auto K) { constexpr int n2 = decltype(K)::value; b[n2] = col[n2 * C::PITCH]; });
+        dft<C::N2, -1>(b);
+    });
+    apply_powers<C::N2, false, true, C::B2>(v, w2);
     static_for<0, C::B2>([&](auto U) {
         constexpr int u = decltype(U)::value;
         cf* b = v + u * C::N2;
         cf* col = tile + ((warp + u * C::WARPS) * C::N2) * C::PITCH + lane;
-        static_for<0, C::N2>([&](auto K) { constexpr int n2 = decltype(K)::value; b[n2] = col[n2 * C::PITCH]; });
-        dft<C::N2, -1>(b);
-        apply_powers<C::N2, false, true>(b, w2);
         static_for<0, C::N2>([&](auto K) {
             constexpr int k2 = decltype(K)::value;
             col[k2 * C::PITCH] = b[brev<C::N2>(k2)];
@@ -354,9 +364,14 @@ ADT_HD void inv_stage2(cf* v, int t, const cf* __restrict__ tw2, cf* tile) {
     static_for<0, C::B2>([&](auto U) {
         constexpr int u = decltype(U)::value;
         cf* b = v + u * C::N2;
-        cf* col = tile + ((warp + u * C::WARPS) * C::N2) * C::PITCH + lane;
+        const cf* col = tile + ((warp + u * C::WARPS) * C::N2) * C::PITCH + lane;
         static_for<0, C::N2>([&](auto K) { constexpr int k2 = decltype(K)::value; b[k2] = col[k2 * C::PITCH]; });
-        apply_powers<C::N2, true, false>(b, w2);
+    });
+    apply_powers<C::N2, true, false, C::B2>(v, w2);
+    static_for<0, C::B2>([&](auto U) {
+        constexpr int u = decltype(U)::value;
+        cf* b = v + u * C::N2;
+        cf* col = tile + ((warp + u * C::WARPS) * C::N2) * C::PITCH + lane;
         dft<C::N2, +1>(b);
         static_for<0, C::N2>([&](auto K) { constexpr int n2 = decltype(K)::value; col[n2 * C::PITCH] = b[brev<C::N2>(n2)]; });
     });
