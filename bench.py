@@ -222,6 +222,8 @@ def main():
 
     dist = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
         import torch
         import torch.distributed as dist_mod
         torch.cuda.set_device(local_rank)
@@ -318,6 +320,14 @@ def main():
         return
 
     peak, peak_src = _peaks()
+    traffic = None
+    try:   # DRAM bytes of one launch from the committed `ncu --set full` capture of this workload
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("workload") == args.workload and channels == 1000:
+            traffic = tj["traffic_bytes_per_launch"]
+    except Exception:
+        pass
     alg_bytes = 8.0 * channels * n_out            # per launch, this rank
     achieved = alg_bytes / (ms_step * 1e-3) / 1e9
     plan = dev.plan
@@ -335,7 +345,8 @@ def main():
                    "parallelism": f"channel-sharded x{world}, no data-path collective",
                    "parity_rms_vs_oracle": max(errs)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "fir_block_kernel",
+                     "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, ncu)",
+                     "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src, "kernel": "fir_block_kernel",
                      "algorithmic_bytes_per_sample": 8,
                      "fp32_tflops_nominal_radix2_count": flops_per_block * blocks / (ms_step * 1e-3) / 1e12},
         "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
