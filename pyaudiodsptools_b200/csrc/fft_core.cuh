@@ -102,6 +102,9 @@ ADT_HD cf cfma(cf a, cf b, cf acc) { return fma_s(a.x, b, fma_s(a.y, mk(-b.y, b.
 
 ADT_HD cf mask_mul(cf a, float h) { return mul_s(h, a); }  // zero-phase (real) mask
 ADT_HD cf mask_mul(cf a, cf h) { return cmul(a, h); }
+// acc + a*h
+ADT_HD cf mask_fma(cf a, float h, cf acc) { return fma_s(h, a, acc); }
+ADT_HD cf mask_fma(cf a, cf h, cf acc) { return fma_s(a.x, h, fma_s(a.y, mk(-h.y, h.x), acc)); }
 
 // cos / sin of 2*pi*q/32 as literals (constexpr trig is not available).
 ADT_HD constexpr float cos32(int q) {
@@ -241,6 +244,69 @@ ADT_HD void apply_powers(cf* v, cf w1) {
     });
 }
 
+// acc + x * conj(p)
+ADT_HD cf cfmac(cf x, cf p, cf acc) { return fma_s(x.x, mk(p.x, -p.y), fma_s(x.y, mk(p.y, p.x), acc)); }
+
+// v[k] *= conj(w1^k) followed by the inverse R-point DFT, with the twiddles FOLDED into the first
+// radix-2 stage: that stage pairs (v[j], v[j+R/2]) with unit twiddle, so
+//     A = v[j]*conj(p_j);  a' = A + v[j+R/2]*conj(p_{j+R/2});  b' = 2A - a'
+// is 5 packed instructions instead of 6 (3 instead of 4 for j = 0).  NB butterflies share the powers.
+template <int R, int NB>
+ADT_HD void twiddle_idft(cf* v, cf w1) {
+    static_assert(R >= 8 && R % 4 == 0, "radix");
+    constexpr int A = R / 4;
+    cf b[4], q[A];
+    b[1] = w1;
+    b[2] = cmul(w1, w1);
+    b[3] = cmul(b[2], w1);
+    q[1] = cmul(b[2], b[2]);
+    static_for<2, A>([&](auto K) {
+        constexpr int a = decltype(K)::value;
+        constexpr int hi = (a & (a - 1)) == 0 ? a / 2 : hibit(a);
+        q[a] = cmul(q[hi], q[a - hi]);
+    });
+    auto power = [&](auto K) {
+        constexpr int k = decltype(K)::value;
+        constexpr int a = k / 4, j = k % 4;
+        if constexpr (a == 0)
+            return b[j];
+        else if constexpr (j == 0)
+            return q[a];
+        else
+            return cmul(q[a], b[j]);
+    };
+    static_for<0, R / 2>([&](auto J) {
+        constexpr int j = decltype(J)::value;
+        const cf p_hi = power(IC<j + R / 2>{});
+        cf p_lo = p_hi;
+        if constexpr (j > 0) p_lo = power(IC<j>{});
+        static_for<0, NB>([&](auto U) {
+            constexpr int o = decltype(U)::value * R;
+            cf a0 = v[o + j];
+            if constexpr (j > 0) a0 = cmulc(a0, p_lo);
+            const cf a1 = cfmac(v[o + j + R / 2], p_hi, a0);
+            v[o + j + R / 2] = fma_s(2.0f, a0, mk(-a1.x, -a1.y));
+            v[o + j] = a1;
+        });
+    });
+    static_for<0, NB>([&](auto U) { dft_stage<R, +1, 2>(v + decltype(U)::value * R); });
+}
+
+// y = IDFT_32(mask .* x) with the mask folded into the first radix-2 stage; x[k] is read from
+// xs[brev<32>(k)] (the layout dft<32,-1> leaves), the result c[r] is at y[brev<32>(r)].
+template <class MaskT, class LoadMask>
+ADT_HD void masked_idft32(const cf* xs, cf* y, LoadMask&& load_mask) {
+    static_for<0, 16>([&](auto J) {
+        constexpr int j = decltype(J)::value;
+        const MaskT h_lo = load_mask(IC<j>{}), h_hi = load_mask(IC<j + 16>{});
+        const cf a0 = mask_mul(xs[brev<32>(j)], h_lo);
+        const cf a1 = mask_fma(xs[brev<32>(j + 16)], h_hi, a0);
+        y[j + 16] = fma_s(2.0f, a0, mk(-a1.x, -a1.y));
+        y[j] = a1;
+    });
+    dft_stage<32, +1, 2>(y);
+}
+
 // ---------------------------------------------------------------------------
 // configuration of one transform size
 // ---------------------------------------------------------------------------
@@ -347,12 +413,7 @@ ADT_HD void mid_stage3(cf* v, int t, const MaskT* __restrict__ mask, cf* tile) {
     static_for<0, 32>([&](auto K) { constexpr int r2 = decltype(K)::value; v[r2] = row[r2]; });
     dft<32, -1>(v);
     cf y[32];
-    static_for<0, 32>([&](auto K) {
-        constexpr int k3 = decltype(K)::value;
-        const cf x = v[brev<32>(k3)];
-        y[k3] = mask_mul(x, mask[k3 * C::T + t]);
-    });
-    dft<32, +1>(y);
+    masked_idft32<MaskT>(v, y, [&](auto K) { return mask[decltype(K)::value * C::T + t]; });
     static_for<0, 32>([&](auto K) { constexpr int r2 = decltype(K)::value; row[r2] = y[brev<32>(r2)]; });
 }
 
@@ -367,12 +428,11 @@ ADT_HD void inv_stage2(cf* v, int t, const cf* __restrict__ tw2, cf* tile) {
         const cf* col = tile + ((warp + u * C::WARPS) * C::N2) * C::PITCH + lane;
         static_for<0, C::N2>([&](auto K) { constexpr int k2 = decltype(K)::value; b[k2] = col[k2 * C::PITCH]; });
     });
-    apply_powers<C::N2, true, false, C::B2>(v, w2);
+    twiddle_idft<C::N2, C::B2>(v, w2);
     static_for<0, C::B2>([&](auto U) {
         constexpr int u = decltype(U)::value;
         cf* b = v + u * C::N2;
         cf* col = tile + ((warp + u * C::WARPS) * C::N2) * C::PITCH + lane;
-        dft<C::N2, +1>(b);
         static_for<0, C::N2>([&](auto K) { constexpr int n2 = decltype(K)::value; col[n2 * C::PITCH] = b[brev<C::N2>(n2)]; });
     });
 }
@@ -391,8 +451,7 @@ ADT_HD void inv_stage1(cf* v, int t, const cf* __restrict__ tw1, const cf* tile)
             constexpr int k1 = decltype(K)::value;
             b[k1] = tile[(k1 * C::N2 + row0) * C::PITCH + lane];
         });
-        apply_powers<C::N1, true, false>(b, tw1[r]);
-        dft<C::N1, +1>(b);
+        twiddle_idft<C::N1, 1>(b, tw1[r]);
     });
 }
 

@@ -141,8 +141,7 @@ ADT_HD void inv16_stage2(cf* v, int t, const cf* __restrict__ tw2, cf* tile) {
     const int r2 = t % C::N3;
     cf* col = tile + (t / C::N3) * 16 * C::PITCH + r2;
     static_for<0, 16>([&](auto K) { constexpr int k2 = decltype(K)::value; v[k2] = col[k2 * C::PITCH]; });
-    apply_powers<16, true, false>(v, tw2[r2]);
-    dft<16, +1>(v);
+    twiddle_idft<16, 1>(v, tw2[r2]);
     static_for<0, 16>([&](auto K) { constexpr int n2 = decltype(K)::value; col[n2 * C::PITCH] = v[brev<16>(n2)]; });
 }
 
@@ -151,8 +150,7 @@ template <class C>
 ADT_HD void inv16_stage1(cf* v, int t, const cf* __restrict__ tw1, const cf* tile) {
     const cf* col = tile + (t / C::N3) * C::PITCH + (t % C::N3);
     static_for<0, 16>([&](auto K) { constexpr int k1 = decltype(K)::value; v[k1] = col[k1 * 16 * C::PITCH]; });
-    apply_powers<16, true, false>(v, tw1[t]);
-    dft<16, +1>(v);
+    twiddle_idft<16, 1>(v, tw1[t]);
 }
 
 template <class C>
