@@ -178,8 +178,7 @@ extern "C" int adt_ctx_create(int device, adt_ctx** out) {
     for (int vi = 0; vi < n_var; ++vi) {
         const FirVariant* v = &vars[vi];
         for (fir_kernel_fn f : {v->cplx, v->real}) {
-            e = cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)(v->smem + (getenv("ADT_FIR_EXTRA_SMEM") ? atoi(getenv("ADT_FIR_EXTRA_SMEM")) : 0)));
+            e = cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->smem);
             if (e != cudaSuccess) {
                 delete ctx;
                 return ADT_ERR_CUDA;
@@ -383,8 +382,7 @@ static int fir_launch(adt_fir* f, cudaStream_t s, const float* x, int64_t in_pit
     const double pf = getenv("ADT_FIR_PREFETCH") ? atof(getenv("ADT_FIR_PREFETCH")) : (f->d.fft_size >= 8192 ? 0.5 : 0.0);
     a.prefetch_ahead = (int)(pf * f->resident_ctas);
     const unsigned grid = (unsigned)a.n_items;
-    static const size_t extra_smem = getenv("ADT_FIR_EXTRA_SMEM") ? (size_t)atoi(getenv("ADT_FIR_EXTRA_SMEM")) : 0;  // occupancy experiments
-    k<<<grid, f->var->threads, f->var->smem + extra_smem, s>>>(a);
+    k<<<grid, f->var->threads, f->var->smem, s>>>(a);
     CK(ctx, cudaGetLastError());
     ctx->launches++;
     return ADT_OK;

@@ -84,6 +84,34 @@ def test_batched_channels_are_independent(gpu_lib, channels):
     assert rms(ys - y) <= 1e-6
 
 
+@pytest.mark.parametrize("chunk", [256, 1000, 2048, 8192, 16384])
+@pytest.mark.parametrize("kind", ["lowcut", "eq3fft"])
+def test_other_chunk_sizes(gpu_lib, chunk, kind):
+    """Chunk sizes beyond the golden set, including one that is not a power of two (the reference only
+    needs C % 4 == 0): streaming apply and whole-buffer mode against the oracle's closed form."""
+    fs = 48000
+    adt.config.initialize(fs, chunk)
+    if kind == "eq3fft":
+        if chunk > 8192:
+            with pytest.raises(ValueError):
+                adt.CreateEQ3BandFFT(120, 3, 900, -5, 7000, 4, channels=3)     # needs an FFT > 16384: rejected, no fallback
+            return
+        dev = adt.CreateEQ3BandFFT(120, 3, 900, -5, 7000, 4, channels=3)
+        taps = oracle.eq3_composite_taps(fs, chunk, 120, 3, 900, -5, 7000, 4)
+    else:
+        dev = adt.CreateLowCutFilter(500, channels=3)
+        taps = oracle.lowcut_taps(fs, chunk, 500)
+    n = 5 * chunk + chunk // 3
+    x = np.random.default_rng(chunk).uniform(-1, 1, (3, n)).astype(np.float32)
+    y = dev.process(x)
+    assert y.shape == (3, 6 * chunk)
+    for ch in range(3):
+        assert rms(y[ch] - oracle.fir_stream_f64(taps, chunk, x[ch])) <= RMS_TOL
+    xp = np.pad(x, ((0, 0), (0, 6 * chunk - n)))
+    ys = np.concatenate([dev.apply(xp[:, i:i + chunk]) for i in range(0, 6 * chunk, chunk)], axis=1)
+    assert rms(ys - y) <= 1e-6
+
+
 def test_eq_batched_stereo_pairs(gpu_lib):
     # BASELINE config 5 shape in miniature: 96 kHz, stereo = two planar rows per stream
     fs, c = 96000, 4096
