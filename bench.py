@@ -186,6 +186,9 @@ def main():
     ap.add_argument("--workload", default="lowcut", choices=sorted(WORKLOADS))
     ap.add_argument("--channels", type=int, default=0, help="override channels per GPU")
     ap.add_argument("--fft-size", type=int, default=0, help="override the planner's FFT size")
+    ap.add_argument("--io", default="f32", choices=["f32", "i16"],
+                    help="sample format at the HBM/PCIe boundary: f32 = the reference's float32 chunks (the "
+                         "BASELINE metric); i16 = 16-bit PCM fused into load/store (SURVEY 8(f) N3, separate mode)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -250,17 +253,24 @@ def main():
     n_out = dev.out_length(n_in)
 
     # synthetic input: uniform(-1,1) float32, seeded per (rank, channel block); 64 distinct rows tiled
-    x_host = ctx.pinned_empty((channels, n_in), np.float32)
+    i16 = args.io == "i16"
+    io_dtype, es = (np.int16, 2) if i16 else (np.float32, 4)
+    x_host = ctx.pinned_empty((channels, n_in), io_dtype)
     base = np.random.default_rng(1234 + rank).uniform(-1, 1, (min(64, channels), n_in)).astype(np.float32)
+    if i16:
+        base = (base * 32767).astype(np.int16)
     for r0 in range(0, channels, base.shape[0]):
         k = min(base.shape[0], channels - r0)
         x_host[r0:r0 + k] = base[:k]
-    y_host = ctx.pinned_empty((channels, n_out), np.float32)
+    y_host = ctx.pinned_empty((channels, n_out), io_dtype)
     dx, dy = ctx.malloc(x_host.nbytes), ctx.malloc(y_host.nbytes)
     ctx.h2d(dx, x_host)
 
     def step():
-        dev.process_device(dx, n_in, n_in, dy, n_out, n_out, channels)
+        if i16:
+            dev.process_device_int16(dx, n_in, n_in, dy, n_out, n_out, channels)
+        else:
+            dev.process_device(dx, n_in, n_in, dy, n_out, n_out, channels)
 
     for _ in range(args.warmup):
         step()
@@ -268,16 +278,19 @@ def main():
     # parity spot check of what is being timed (row 0 and last row vs the oracle closed form)
     import oracle
     taps = dev.taps
-    yrow = np.empty((1, n_out), np.float32)
+    yrow = np.empty((1, n_out), io_dtype)
     errs = []
     for row in (0, channels - 1):
-        ctx.d2h(yrow, dy + row * n_out * 4)
+        ctx.d2h(yrow, dy + row * n_out * es)
         from scipy.signal import fftconvolve
-        full = fftconvolve(x_host[row].astype(np.float64), taps)
+        xin = x_host[row].astype(np.float32) / 32768 if i16 else x_host[row]
+        full = fftconvolve(xin.astype(np.float64), taps)
         want = np.zeros(n_out); d = oracle.stream_delay(chunk)
         want[d:] = full[: n_out - d]
-        errs.append(float(np.sqrt(np.mean((yrow[0] - want) ** 2))))
-    assert max(errs) <= 1e-5, f"parity broken in bench: rms {errs}"
+        got = yrow[0].astype(np.float64) / 32767 if i16 else yrow[0]
+        errs.append(float(np.sqrt(np.mean((got - want) ** 2))))
+    # float32 I/O: north_star tolerance 1e-5 RMS.  int16 I/O: truncation to 16 bits adds ~1/(32767*sqrt(3)) RMS.
+    assert max(errs) <= (3e-5 if i16 else 1e-5), f"parity broken in bench: rms {errs}"
 
     e0, e1 = ctx.event(), ctx.event()
     sampler = ClockSampler(local_rank)
@@ -302,17 +315,19 @@ def main():
     if not args.no_e2e:
         dev_b = ctor(*ctor_args, channels=1, device=local_rank, fft_size=args.fft_size or None)
         e2e_steps = max(2, min(args.steps, 5))
-        dev_b.process(x_host, out=y_host)      # warm-up (allocates the staging buffers)
+        run_e2e = (lambda: dev_b.process_int16(x_host, out=y_host)) if i16 else (lambda: dev_b.process(x_host, out=y_host))
+        run_e2e()                              # warm-up (allocates the staging buffers)
         barrier(); ctx.sync()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            dev_b.process(x_host, out=y_host)  # returns when y_host is complete
+            run_e2e()                          # returns when y_host is complete
         dt = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
         barrier()
         e2e = {"value": samples_step_all / dt / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": int(x_host.nbytes),
                "d2h_bytes_per_step": int(y_host.nbytes), "steps": e2e_steps, "ms_per_step": dt * 1e3,
-               "api": f"{ctor.__name__}(...).process(pinned host array)"}
-        assert float(np.sqrt(np.mean((y_host[channels - 1] - want) ** 2))) <= 1e-5, "e2e parity broken"
+               "api": f"{ctor.__name__}(...).{'process_int16' if i16 else 'process'}(pinned host array)"}
+        got = y_host[channels - 1].astype(np.float64) / 32767 if i16 else y_host[channels - 1]
+        assert float(np.sqrt(np.mean((got - want) ** 2))) <= (3e-5 if i16 else 1e-5), "e2e parity broken"
 
     if rank != 0:
         if dist:
@@ -324,11 +339,11 @@ def main():
     try:   # DRAM bytes of one launch from the committed `ncu --set full` capture of this workload
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
             tj = json.load(f)
-        if tj.get("workload") == args.workload and channels == 1000:
+        if tj.get("workload") == args.workload and channels == 1000 and not i16:
             traffic = tj["traffic_bytes_per_launch"]
     except Exception:
         pass
-    alg_bytes = 8.0 * channels * n_out            # per launch, this rank
+    alg_bytes = 2.0 * es * channels * n_out       # per launch, this rank: one read + one write per sample
     achieved = alg_bytes / (ms_step * 1e-3) / 1e9
     plan = dev.plan
     flops_per_block = 2 * (5.0 * plan.fft_size * np.log2(plan.fft_size)) + 6 * plan.fft_size
@@ -336,8 +351,9 @@ def main():
     line = {
         "metric": "Msamples/s overlap-add FFT filter, chunk=%d" % chunk, "value": value, "unit": "Msamples/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "channels_per_gpu": channels, "samples_per_channel": n_in,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 compute, int16 PCM I/O (separate mode, SURVEY 8(f) N3)" if i16 else "f32", "data": "synthetic",
+        "config": {"workload": desc + (" [16-bit PCM in/out, conversions fused]" if i16 else ""), "channels_per_gpu": channels, "samples_per_channel": n_in,
                    "out_samples_per_channel": n_out, "chunk": chunk, "fft_size": plan.fft_size, "hop": plan.hop,
                    "mask": "real" if plan.mask_is_real else "complex", "n_taps": plan.n_taps,
                    "l2": "inputs larger than L2 (%.2f GB read + %.2f GB written per pass vs 126 MB L2)" % (
@@ -347,7 +363,7 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_unit": "bytes per launch (dram read+write, ncu)",
                      "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src, "kernel": "fir_block_kernel",
-                     "algorithmic_bytes_per_sample": 8,
+                     "algorithmic_bytes_per_sample": 2 * es,
                      "fp32_tflops_nominal_radix2_count": flops_per_block * blocks / (ms_step * 1e-3) / 1e12},
         "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
     }

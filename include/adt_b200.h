@@ -111,6 +111,14 @@ int adt_fir_process_dev(adt_fir* fir, const float* x_dev, int64_t in_pitch, int6
 int adt_fir_process_host(adt_fir* fir, const float* x_host, int64_t in_pitch, int64_t n_in, float* y_host,
                          int64_t out_pitch, int64_t n_out, int32_t n_rows);
 
+/* 16-bit PCM variants: the WAV conversions either side of the path are fused into
+ * the kernel's load and store — x = int16/32768 (Utility.py:236-237), y = (int16)(y*32767) with C
+ * truncation (Utility.py:306) — which halves HBM and PCIe bytes.  Reported as a separate mode. */
+int adt_fir_process_dev_i16(adt_fir* fir, const int16_t* x_dev, int64_t in_pitch, int64_t n_in, int16_t* y_dev,
+                            int64_t out_pitch, int64_t n_out, int32_t n_rows);
+int adt_fir_process_host_i16(adt_fir* fir, const int16_t* x_host, int64_t in_pitch, int64_t n_in, int16_t* y_host,
+                             int64_t out_pitch, int64_t n_out, int32_t n_rows);
+
 /* Streaming step == one reference .apply(): in/out are [n_channels][chunk]
  * contiguous; updates the device-resident history (2 buffers of back+chunk
  * samples per channel).  Output i corresponds to input i-1 (latency = chunk). */

@@ -58,6 +58,8 @@ PROTOTYPES = {
     "adt_fir_destroy": (C.c_int, [_P]),
     "adt_fir_process_dev": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int32]),
     "adt_fir_process_host": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int32]),
+    "adt_fir_process_dev_i16": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int32]),
+    "adt_fir_process_host_i16": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int32]),
     "adt_fir_apply_host": (C.c_int, [_P, _P, _P]),
     "adt_fir_apply_dev": (C.c_int, [_P, _P, _P]),
     "adt_fir_reset": (C.c_int, [_P]),

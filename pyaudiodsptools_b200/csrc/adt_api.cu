@@ -82,6 +82,7 @@ struct FirVariant {
     int n, threads;
     size_t smem;
     fir_kernel_fn cplx, real;
+    fir_kernel_fn cplx_i16, real_i16;  // 16-bit PCM in/out (IoI16)
     void (*build)(const float* mask, bool real_only, HostTables& out);
 };
 
@@ -95,6 +96,8 @@ FirVariant make_variant32(const char* name) {
     v.smem = (size_t)C::TILE * sizeof(cf);
     v.cplx = fir_block_kernel<C, cf, MIN_CTAS>;
     v.real = fir_block_kernel<C, float, MIN_CTAS>;
+    v.cplx_i16 = fir_block_kernel<C, cf, MIN_CTAS, IoI16>;
+    v.real_i16 = fir_block_kernel<C, float, MIN_CTAS, IoI16>;
     v.build = [](const float* mask, bool real_only, HostTables& out) {
         out.tw1 = build_tw1<C>();
         out.tw2 = build_tw2<C>();
@@ -113,6 +116,8 @@ FirVariant make_variant16(const char* name) {
     v.smem = (size_t)C::TILE * sizeof(cf);
     v.cplx = fir16_block_kernel<C, cf, MIN_CTAS>;
     v.real = fir16_block_kernel<C, float, MIN_CTAS>;
+    v.cplx_i16 = fir16_block_kernel<C, cf, MIN_CTAS, IoI16>;
+    v.real_i16 = fir16_block_kernel<C, float, MIN_CTAS, IoI16>;
     v.build = [](const float* mask, bool real_only, HostTables& out) {
         out.tw1 = build16_tw1<C>();
         out.tw2 = build16_tw2<C>();
@@ -177,7 +182,7 @@ extern "C" int adt_ctx_create(int device, adt_ctx** out) {
     const FirVariant* vars = all_variants(&n_var);
     for (int vi = 0; vi < n_var; ++vi) {
         const FirVariant* v = &vars[vi];
-        for (fir_kernel_fn f : {v->cplx, v->real}) {
+        for (fir_kernel_fn f : {v->cplx, v->real, v->cplx_i16, v->real_i16}) {
             e = cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->smem);
             if (e != cudaSuccess) {
                 delete ctx;
@@ -343,8 +348,8 @@ struct adt_fir {
     size_t out_cap[ADT_COPY_STREAMS] = {};
 };
 
-static int fir_launch(adt_fir* f, cudaStream_t s, const float* x, int64_t in_pitch, int64_t n_in, int64_t in_shift,
-                      float* y, int64_t out_pitch, int64_t n_out, int32_t n_rows) {
+static int fir_launch(adt_fir* f, cudaStream_t s, const void* x, int64_t in_pitch, int64_t n_in, int64_t in_shift,
+                      void* y, int64_t out_pitch, int64_t n_out, int32_t n_rows, bool i16 = false) {
     adt_ctx* ctx = f->ctx;
     if (n_rows <= 0 || n_out <= 0) return ADT_OK;
     const int64_t blocks = (n_out + f->d.hop - 1) / f->d.hop;
@@ -369,7 +374,8 @@ static int fir_launch(adt_fir* f, cudaStream_t s, const float* x, int64_t in_pit
     a.g.n_out = n_out;
     a.g.in_pitch = in_pitch;
     a.g.out_pitch = out_pitch;
-    fir_kernel_fn k = f->d.mask_is_real ? f->var->real : f->var->cplx;
+    fir_kernel_fn k = i16 ? (f->d.mask_is_real ? f->var->real_i16 : f->var->cplx_i16)
+                          : (f->d.mask_is_real ? f->var->real : f->var->cplx);
     if (a.n_items > 0x7fffffffLL)
         return adt_set_error(ctx, ADT_ERR_UNSUPPORTED, "too many work items: %lld", (long long)a.n_items);
     if (f->resident_ctas == 0) {  // CTAs in flight at once = how far ahead the L2 prefetch looks
@@ -478,12 +484,21 @@ static int check_buffers(adt_fir* f, const void* x, int64_t in_pitch, int64_t n_
     return ADT_OK;
 }
 
-extern "C" int adt_fir_process_dev(adt_fir* f, const float* x, int64_t in_pitch, int64_t n_in, float* y,
-                                   int64_t out_pitch, int64_t n_out, int32_t n_rows) {
+static int fir_process_dev_impl(adt_fir* f, const void* x, int64_t in_pitch, int64_t n_in, void* y, int64_t out_pitch,
+                                int64_t n_out, int32_t n_rows, bool i16) {
     int rc = check_buffers(f, x, in_pitch, n_in, y, out_pitch, n_out, n_rows);
     if (rc) return rc;
     CK(f->ctx, cudaSetDevice(f->ctx->device));
-    return fir_launch(f, f->ctx->stream, x, in_pitch, n_in, 0, y, out_pitch, n_out, n_rows);
+    return fir_launch(f, f->ctx->stream, x, in_pitch, n_in, 0, y, out_pitch, n_out, n_rows, i16);
+}
+
+extern "C" int adt_fir_process_dev(adt_fir* f, const float* x, int64_t in_pitch, int64_t n_in, float* y,
+                                   int64_t out_pitch, int64_t n_out, int32_t n_rows) {
+    return fir_process_dev_impl(f, x, in_pitch, n_in, y, out_pitch, n_out, n_rows, false);
+}
+extern "C" int adt_fir_process_dev_i16(adt_fir* f, const int16_t* x, int64_t in_pitch, int64_t n_in, int16_t* y,
+                                       int64_t out_pitch, int64_t n_out, int32_t n_rows) {
+    return fir_process_dev_impl(f, x, in_pitch, n_in, y, out_pitch, n_out, n_rows, true);
 }
 
 static int ensure_cap(adt_ctx* ctx, float** p, size_t* cap, size_t need) {
@@ -496,16 +511,20 @@ static int ensure_cap(adt_ctx* ctx, float** p, size_t* cap, size_t need) {
     return ADT_OK;
 }
 
-extern "C" int adt_fir_process_host(adt_fir* f, const float* x, int64_t in_pitch, int64_t n_in, float* y,
-                                    int64_t out_pitch, int64_t n_out, int32_t n_rows) {
-    int rc = check_buffers(f, x, in_pitch, n_in, y, out_pitch, n_out, n_rows);
+// H2D -> kernel -> D2H pipelined over row groups on the copy streams; es = bytes per sample.
+static int fir_process_host_impl(adt_fir* f, const void* xv, int64_t in_pitch, int64_t n_in, void* yv,
+                                 int64_t out_pitch, int64_t n_out, int32_t n_rows, bool i16) {
+    int rc = check_buffers(f, xv, in_pitch, n_in, yv, out_pitch, n_out, n_rows);
     if (rc) return rc;
     adt_ctx* ctx = f->ctx;
     if (n_rows == 0 || n_out == 0) return ADT_OK;
     CK(ctx, cudaSetDevice(ctx->device));
-    // row groups of ~48 MB of input, an even number of rows (channel pairs stay together)
-    const int64_t din_pitch = (n_in + 31) / 32 * 32, dout_pitch = (n_out + 31) / 32 * 32;
-    int64_t g_rows = (int64_t)(48u << 20) / (int64_t)((din_pitch > dout_pitch ? din_pitch : dout_pitch) * sizeof(float));
+    const size_t es = i16 ? sizeof(int16_t) : sizeof(float);
+    const char* x = static_cast<const char*>(xv);
+    char* y = static_cast<char*>(yv);
+    // row groups of ~48 MB, an even number of rows (channel pairs stay together); pitches keep 128-byte rows
+    const int64_t din_pitch = (n_in + 63) / 64 * 64, dout_pitch = (n_out + 63) / 64 * 64;
+    int64_t g_rows = (int64_t)(48u << 20) / (int64_t)((din_pitch > dout_pitch ? din_pitch : dout_pitch) * es);
     g_rows = g_rows < 2 ? 2 : (g_rows & ~1LL);
     if (g_rows > n_rows) g_rows = (n_rows + 1) & ~1LL;
     // everything queued on the context stream so far must be done before the copy streams start
@@ -516,24 +535,32 @@ extern "C" int adt_fir_process_host(adt_fir* f, const float* x, int64_t in_pitch
         cudaStream_t s = ctx->copy_stream[si];
         const int32_t rows = (int32_t)((n_rows - r0) < g_rows ? (n_rows - r0) : g_rows);
         if (gi < ADT_COPY_STREAMS) CK(ctx, cudaStreamWaitEvent(s, ctx->fence, 0));
-        if (f->in_cap[si] < (size_t)g_rows * din_pitch * sizeof(float) ||
-            f->out_cap[si] < (size_t)g_rows * dout_pitch * sizeof(float)) {
+        if (f->in_cap[si] < (size_t)g_rows * din_pitch * es || f->out_cap[si] < (size_t)g_rows * dout_pitch * es) {
             CK(ctx, cudaStreamSynchronize(s));
-            rc = ensure_cap(ctx, &f->d_in[si], &f->in_cap[si], (size_t)g_rows * din_pitch * sizeof(float));
+            rc = ensure_cap(ctx, &f->d_in[si], &f->in_cap[si], (size_t)g_rows * din_pitch * es);
             if (rc) return rc;
-            rc = ensure_cap(ctx, &f->d_out[si], &f->out_cap[si], (size_t)g_rows * dout_pitch * sizeof(float));
+            rc = ensure_cap(ctx, &f->d_out[si], &f->out_cap[si], (size_t)g_rows * dout_pitch * es);
             if (rc) return rc;
         }
         if (n_in > 0)
-            CK(ctx, cudaMemcpy2DAsync(f->d_in[si], din_pitch * sizeof(float), x + r0 * in_pitch, in_pitch * sizeof(float),
-                                      n_in * sizeof(float), rows, cudaMemcpyHostToDevice, s));
-        rc = fir_launch(f, s, f->d_in[si], din_pitch, n_in, 0, f->d_out[si], dout_pitch, n_out, rows);
+            CK(ctx, cudaMemcpy2DAsync(f->d_in[si], din_pitch * es, x + (size_t)r0 * in_pitch * es, in_pitch * es,
+                                      n_in * es, rows, cudaMemcpyHostToDevice, s));
+        rc = fir_launch(f, s, f->d_in[si], din_pitch, n_in, 0, f->d_out[si], dout_pitch, n_out, rows, i16);
         if (rc) return rc;
-        CK(ctx, cudaMemcpy2DAsync(y + r0 * out_pitch, out_pitch * sizeof(float), f->d_out[si], dout_pitch * sizeof(float),
-                                  n_out * sizeof(float), rows, cudaMemcpyDeviceToHost, s));
+        CK(ctx, cudaMemcpy2DAsync(y + (size_t)r0 * out_pitch * es, out_pitch * es, f->d_out[si], dout_pitch * es,
+                                  n_out * es, rows, cudaMemcpyDeviceToHost, s));
     }
     for (int i = 0; i < ADT_COPY_STREAMS; ++i) CK(ctx, cudaStreamSynchronize(ctx->copy_stream[i]));
     return ADT_OK;
+}
+
+extern "C" int adt_fir_process_host(adt_fir* f, const float* x, int64_t in_pitch, int64_t n_in, float* y,
+                                    int64_t out_pitch, int64_t n_out, int32_t n_rows) {
+    return fir_process_host_impl(f, x, in_pitch, n_in, y, out_pitch, n_out, n_rows, false);
+}
+extern "C" int adt_fir_process_host_i16(adt_fir* f, const int16_t* x, int64_t in_pitch, int64_t n_in, int16_t* y,
+                                        int64_t out_pitch, int64_t n_out, int32_t n_rows) {
+    return fir_process_host_impl(f, x, in_pitch, n_in, y, out_pitch, n_out, n_rows, true);
 }
 
 // One streaming step on device buffers: hist[cur] = [last `back` samples | new chunk].

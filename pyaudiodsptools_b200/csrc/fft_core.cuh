@@ -338,17 +338,34 @@ struct FirGeom {
     long long in_pitch, out_pitch;  // row pitches in floats
 };
 
+// Sample formats at the HBM boundary.  F32: the reference's float32 chunks.  I16: 16-bit PCM fused
+// into the load/store — x = int16/32768 on load (Utility.py:236-237, MonoWavToNumpyFloat) and
+// int16(y*32767) with C truncation on store (Utility.py:306, NumpyFloatToWav); halves HBM bytes.
+struct IoF32 {
+    typedef float elem;
+    ADT_HD static float load(const float* p) { return *p; }
+    ADT_HD static void store(float* p, float v) { *p = v; }
+};
+struct IoI16 {
+    typedef short elem;
+    ADT_HD static float load(const short* p) { return (float)*p * (1.0f / 32768.0f); }
+    ADT_HD static void store(short* p, float v) {
+        // numpy's float32 -> int16 astype on x86: truncate toward zero to int32, keep the low 16 bits
+        *p = (short)(int)(v * 32767.0f);
+    }
+};
+
 // ---- phase 0: global -> registers (stage-1 layout) -------------------------
-template <class C>
-ADT_HD void load_window(cf* v, int t, const float* __restrict__ xa, const float* __restrict__ xb,
-                        long long ws, long long n_in) {
+template <class C, class IO = IoF32>
+ADT_HD void load_window(cf* v, int t, const typename IO::elem* __restrict__ xa,
+                        const typename IO::elem* __restrict__ xb, long long ws, long long n_in) {
     const bool interior = (ws >= 0) && (ws + C::N <= n_in);
     if (interior) {
         static_for<0, C::B1>([&](auto U) {
             static_for<0, C::N1>([&](auto K) {
                 constexpr int u = decltype(U)::value, n1 = decltype(K)::value;
                 const long long s = ws + n1 * C::M1 + t + u * C::T;
-                v[u * C::N1 + n1] = mk(xa[s], xb ? xb[s] : 0.0f);
+                v[u * C::N1 + n1] = mk(IO::load(xa + s), xb ? IO::load(xb + s) : 0.0f);
             });
         });
     } else {
@@ -357,7 +374,7 @@ ADT_HD void load_window(cf* v, int t, const float* __restrict__ xa, const float*
                 constexpr int u = decltype(U)::value, n1 = decltype(K)::value;
                 const long long s = ws + n1 * C::M1 + t + u * C::T;
                 const bool ok = (s >= 0) && (s < n_in);
-                v[u * C::N1 + n1] = mk(ok ? xa[s] : 0.0f, (ok && xb) ? xb[s] : 0.0f);
+                v[u * C::N1 + n1] = mk(ok ? IO::load(xa + s) : 0.0f, (ok && xb) ? IO::load(xb + s) : 0.0f);
             });
         });
     }
@@ -459,13 +476,13 @@ ADT_HD void inv_stage1(cf* v, int t, const cf* __restrict__ tw1, const cf* tile)
 // z[n], n = n1*M1 + t + u*T, goes to y[m0 + n - n0] when 0 <= n - n0 < hop and
 // the stream index is below n_out.  `lim` = min(hop, n_out - m0) folds both
 // upper bounds into one unsigned compare per element.
-template <class C>
-ADT_HD void store_slice(const cf* v, int t, float* __restrict__ ya, float* __restrict__ yb,
+template <class C, class IO = IoF32>
+ADT_HD void store_slice(const cf* v, int t, typename IO::elem* __restrict__ ya, typename IO::elem* __restrict__ yb,
                         long long m0, const FirGeom& g) {
     const long long room = g.n_out - m0;
     const unsigned lim = (unsigned)(room < (long long)g.hop ? (room < 0 ? 0 : room) : g.hop);
-    float* pa = ya + (m0 - g.n0) + t;
-    float* pb = yb ? yb + (m0 - g.n0) + t : nullptr;
+    typename IO::elem* pa = ya + (m0 - g.n0) + t;
+    typename IO::elem* pb = yb ? yb + (m0 - g.n0) + t : nullptr;
     const int jt = t - g.n0;
     static_for<0, C::B1>([&](auto U) {
         static_for<0, C::N1>([&](auto K) {
@@ -473,8 +490,8 @@ ADT_HD void store_slice(const cf* v, int t, float* __restrict__ ya, float* __res
             constexpr int off = n1 * C::M1 + u * C::T;
             const cf z = v[u * C::N1 + brev<C::N1>(n1)];
             const bool ok = (unsigned)(jt + off) < lim;
-            if (ok) pa[off] = z.x;
-            if (ok && pb) pb[off] = z.y;
+            if (ok) IO::store(pa + off, z.x);
+            if (ok && pb) IO::store(pb + off, z.y);
         });
     });
 }

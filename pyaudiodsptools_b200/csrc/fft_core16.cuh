@@ -43,22 +43,22 @@ struct Fir16Cfg {
     ADT_HD static constexpr int s3_half(int t) { return N3 == 32 ? ((t >> 4) & 1) : 0; }
 };
 
-template <class C>
-ADT_HD void load_window16(cf* v, int t, const float* __restrict__ xa, const float* __restrict__ xb, long long ws,
-                          long long n_in) {
+template <class C, class IO = IoF32>
+ADT_HD void load_window16(cf* v, int t, const typename IO::elem* __restrict__ xa,
+                          const typename IO::elem* __restrict__ xb, long long ws, long long n_in) {
     const bool interior = (ws >= 0) && (ws + C::N <= n_in);
     if (interior) {
         static_for<0, 16>([&](auto K) {
             constexpr int n1 = decltype(K)::value;
             const long long s = ws + n1 * C::M1 + t;
-            v[n1] = mk(xa[s], xb ? xb[s] : 0.0f);
+            v[n1] = mk(IO::load(xa + s), xb ? IO::load(xb + s) : 0.0f);
         });
     } else {
         static_for<0, 16>([&](auto K) {
             constexpr int n1 = decltype(K)::value;
             const long long s = ws + n1 * C::M1 + t;
             const bool ok = (s >= 0) && (s < n_in);
-            v[n1] = mk(ok ? xa[s] : 0.0f, (ok && xb) ? xb[s] : 0.0f);
+            v[n1] = mk(ok ? IO::load(xa + s) : 0.0f, (ok && xb) ? IO::load(xb + s) : 0.0f);
         });
     }
 }
@@ -153,21 +153,21 @@ ADT_HD void inv16_stage1(cf* v, int t, const cf* __restrict__ tw1, const cf* til
     twiddle_idft<16, 1>(v, tw1[t]);
 }
 
-template <class C>
-ADT_HD void store_slice16(const cf* v, int t, float* __restrict__ ya, float* __restrict__ yb, long long m0,
-                          const FirGeom& g) {
+template <class C, class IO = IoF32>
+ADT_HD void store_slice16(const cf* v, int t, typename IO::elem* __restrict__ ya, typename IO::elem* __restrict__ yb,
+                          long long m0, const FirGeom& g) {
     const long long room = g.n_out - m0;
     const unsigned lim = (unsigned)(room < (long long)g.hop ? (room < 0 ? 0 : room) : g.hop);
-    float* pa = ya + (m0 - g.n0) + t;
-    float* pb = yb ? yb + (m0 - g.n0) + t : nullptr;
+    typename IO::elem* pa = ya + (m0 - g.n0) + t;
+    typename IO::elem* pb = yb ? yb + (m0 - g.n0) + t : nullptr;
     const int jt = t - g.n0;
     static_for<0, 16>([&](auto K) {
         constexpr int n1 = decltype(K)::value;
         constexpr int off = n1 * C::M1;
         const cf z = v[brev<16>(n1)];
         const bool ok = (unsigned)(jt + off) < lim;
-        if (ok) pa[off] = z.x;
-        if (ok && pb) pb[off] = z.y;
+        if (ok) IO::store(pa + off, z.x);
+        if (ok && pb) IO::store(pb + off, z.y);
     });
 }
 

@@ -14,8 +14,8 @@
 namespace adt {
 
 struct FirKernelArgs {
-    const float* x;        // [n_rows][in_pitch]
-    float* y;              // [n_rows][out_pitch]
+    const void* x;         // [n_rows][in_pitch]  float32 (IoF32) or int16 (IoI16)
+    void* y;               // [n_rows][out_pitch]
     const void* mask;      // kernel-order mask / coefS table (float or float2 per bin), 1/N folded in
     const cf* coef_x;      // 16-point variant with N3 = 32 only: cross coefficients Hd * W32^(+-j)
     const cf* tw1;         // [M1]
@@ -29,20 +29,24 @@ struct FirKernelArgs {
 
 // Work item -> (time block, channel pair).  Time block is the fast index so CTAs that run
 // concurrently read overlapping windows of the same rows (the overlap is served by L2).
+template <class E>
 struct FirItem {
-    const float *xa, *xb;
-    float *ya, *yb;
+    const E *xa, *xb;
+    E *ya, *yb;
     long long m0, ws;
 };
-__device__ __forceinline__ FirItem fir_item(const FirKernelArgs& a, long long item) {
-    FirItem it;
+template <class E>
+__device__ __forceinline__ FirItem<E> fir_item(const FirKernelArgs& a, long long item) {
+    FirItem<E> it;
     const int blk = (int)(item % a.blocks_per_row);
     const int row_a = 2 * (int)(item / a.blocks_per_row), row_b = row_a + 1;
     const bool has_b = row_b < a.n_rows;
-    it.xa = a.x + (long long)row_a * a.g.in_pitch;
-    it.xb = has_b ? a.x + (long long)row_b * a.g.in_pitch : nullptr;
-    it.ya = a.y + (long long)row_a * a.g.out_pitch;
-    it.yb = has_b ? a.y + (long long)row_b * a.g.out_pitch : nullptr;
+    const E* x = static_cast<const E*>(a.x);
+    E* y = static_cast<E*>(a.y);
+    it.xa = x + (long long)row_a * a.g.in_pitch;
+    it.xb = has_b ? x + (long long)row_b * a.g.in_pitch : nullptr;
+    it.ya = y + (long long)row_a * a.g.out_pitch;
+    it.yb = has_b ? y + (long long)row_b * a.g.out_pitch : nullptr;
     it.m0 = (long long)blk * a.g.hop;
     it.ws = it.m0 - a.g.back + a.g.in_shift;
     return it;
@@ -50,33 +54,35 @@ __device__ __forceinline__ FirItem fir_item(const FirKernelArgs& a, long long it
 
 // Warm L2 with the window of the item `ahead` positions later in launch order (about one wave of
 // resident CTAs): by the time that CTA starts, its 64 loads per thread hit L2 instead of HBM.
-template <int N, int T>
+template <int N, int T, class E>
 __device__ __forceinline__ void fir_prefetch_l2(const FirKernelArgs& a, long long item, int t) {
     if (a.prefetch_ahead <= 0) return;
     const long long nxt = item + a.prefetch_ahead;
     if (nxt >= a.n_items) return;
-    const FirItem it = fir_item(a, nxt);
-    // 2 rows x N floats = 2 * N / 32 lines of 128 B
-    constexpr int LINES = N / 32;
+    const FirItem<E> it = fir_item<E>(a, nxt);
+    // 2 rows x N samples, one prefetch per 128-byte line
+    constexpr int PER_LINE = 128 / (int)sizeof(E);
+    constexpr int LINES = N / PER_LINE;
     for (int l = t; l < 2 * LINES; l += T) {
-        const float* base = (l < LINES) ? it.xa : it.xb;
-        const long long s = it.ws + (long long)(l % LINES) * 32;
+        const E* base = (l < LINES) ? it.xa : it.xb;
+        const long long s = it.ws + (long long)(l % LINES) * PER_LINE;
         if (base && s >= 0 && s < a.g.n_in) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + s));
     }
 }
 
 // One CTA per work item.  (A persistent CTA-loop over items was measured 15 % slower on B200 — with
 // or without start skew — and is not used)
-template <class C, class MaskT, int MIN_CTAS>
+template <class C, class MaskT, int MIN_CTAS, class IO = IoF32>
 __global__ void __launch_bounds__(C::T, MIN_CTAS) fir_block_kernel(const FirKernelArgs a) {
+    typedef typename IO::elem E;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cf* tile = reinterpret_cast<cf*>(smem_raw);
     const int t = threadIdx.x;
     const long long item = blockIdx.x;
-    const FirItem it = fir_item(a, item);
+    const FirItem<E> it = fir_item<E>(a, item);
     cf v[32];
-    load_window<C>(v, t, it.xa, it.xb, it.ws, a.g.n_in);
-    fir_prefetch_l2<C::N, C::T>(a, item, t);
+    load_window<C, IO>(v, t, it.xa, it.xb, it.ws, a.g.n_in);
+    fir_prefetch_l2<C::N, C::T, E>(a, item, t);
     fwd_stage1<C>(v, t, a.tw1, tile);
     __syncthreads();
     fwd_stage2<C>(v, t, a.tw2, tile);
@@ -86,20 +92,21 @@ __global__ void __launch_bounds__(C::T, MIN_CTAS) fir_block_kernel(const FirKern
     inv_stage2<C>(v, t, a.tw2, tile);
     __syncthreads();
     inv_stage1<C>(v, t, a.tw1, tile);
-    store_slice<C>(v, t, it.ya, it.yb, it.m0, a.g);
+    store_slice<C, IO>(v, t, it.ya, it.yb, it.m0, a.g);
 }
 
 // 16 points per thread (fft_core16.cuh): 512 threads at <= 64 registers -> 32 warps per SM.
-template <class C, class MaskT, int MIN_CTAS>
+template <class C, class MaskT, int MIN_CTAS, class IO = IoF32>
 __global__ void __launch_bounds__(C::T, MIN_CTAS) fir16_block_kernel(const FirKernelArgs a) {
+    typedef typename IO::elem E;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cf* tile = reinterpret_cast<cf*>(smem_raw);
     const int t = threadIdx.x;
     const long long item = blockIdx.x;
-    const FirItem it = fir_item(a, item);
+    const FirItem<E> it = fir_item<E>(a, item);
     cf v[16];
-    load_window16<C>(v, t, it.xa, it.xb, it.ws, a.g.n_in);
-    fir_prefetch_l2<C::N, C::T>(a, item, t);
+    load_window16<C, IO>(v, t, it.xa, it.xb, it.ws, a.g.n_in);
+    fir_prefetch_l2<C::N, C::T, E>(a, item, t);
     fwd16_stage1<C>(v, t, a.tw1, tile);
     __syncthreads();
     fwd16_stage2<C>(v, t, a.tw2, tile);
@@ -109,7 +116,7 @@ __global__ void __launch_bounds__(C::T, MIN_CTAS) fir16_block_kernel(const FirKe
     inv16_stage2<C>(v, t, a.tw2, tile);
     __syncthreads();
     inv16_stage1<C>(v, t, a.tw1, tile);
-    store_slice16<C>(v, t, it.ya, it.yb, it.m0, a.g);
+    store_slice16<C, IO>(v, t, it.ya, it.yb, it.m0, a.g);
 }
 
 }  // namespace adt

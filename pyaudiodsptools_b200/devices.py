@@ -88,6 +88,28 @@ class _FirDevice:
                                                            n_out, rows))
         return out[0] if one_d else out
 
+    def process_int16(self, x, out=None):
+        """16-bit PCM in and out: equals ``(process(x / 32768) * 32767).astype(int16)``, i.e. the reference's
+        MonoWavToNumpyFloat -> chunks -> apply -> CombineChunks -> NumpyFloatToWav chain (Utility.py:218-238,
+        278-312) with both conversions fused into the kernel.  x: int16 [n] or [rows, n]."""
+        x = np.asarray(x)
+        if x.dtype != np.int16:
+            raise TypeError("process_int16 takes int16 samples")
+        one_d = x.ndim == 1
+        x2 = np.ascontiguousarray(x.reshape(1, -1) if one_d else x)
+        rows, n = x2.shape
+        n_out = self.out_length(n)
+        if out is None:
+            out = np.empty((rows, n_out), dtype=np.int16)
+        assert out.shape == (rows, n_out) and out.dtype == np.int16 and out.flags["C_CONTIGUOUS"]
+        self._ctx.check(self._ctx.lib.adt_fir_process_host_i16(self._h, x2.ctypes.data, n, n, out.ctypes.data, n_out,
+                                                               n_out, rows))
+        return out[0] if one_d else out
+
+    def process_device_int16(self, x_dev, in_pitch, n_in, y_dev, out_pitch, n_out, rows):
+        self._ctx.check(self._ctx.lib.adt_fir_process_dev_i16(self._h, x_dev, in_pitch, n_in, y_dev, out_pitch,
+                                                              n_out, rows))
+
     def process_device(self, x_dev: int, in_pitch: int, n_in: int, y_dev: int, out_pitch: int, n_out: int, rows: int):
         """Whole-buffer mode on device pointers (async on the context stream)."""
         self._ctx.check(self._ctx.lib.adt_fir_process_dev(self._h, x_dev, in_pitch, n_in, y_dev, out_pitch, n_out,

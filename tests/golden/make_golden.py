@@ -105,6 +105,27 @@ def main():
                     numpy=numpy_version, source="EffectEQ3Band.py:90-180")
         _save(f"eq3biquad_{tag}", meta, x=x, **{k: np.concatenate(v) for k, v in outs.items()})
 
+    # --- 16-bit PCM end to end: the Example1.py / Example2.py chains with their WAV
+    #     conversions, Utility.py:218-238 (int16 -> float32/32768) and :306 ((y*32767).astype(int16))
+    import wave
+    ref.config.initialize(44100, 4096)
+    with wave.open(os.path.join(REF, "TestFile16BitMono.wav")) as w:
+        pcm = np.frombuffer(w.readframes(w.getnframes()), dtype=np.int16)[20000:20000 + 8 * 4096].copy()
+    dev = ref.CreateLowCutFilter(800)
+    yf = _run_chunks(dev, pcm.astype("float32") / 32768, 4096)
+    _save("lowcut800_c4096_wav_int16", dict(kind="lowcut", fs=44100, chunk=4096, args=[800], numpy=numpy_version,
+                                             source="Example1.py chain incl. Utility.py:236-237 and :306"),
+          x=pcm, y=(yf * 32767).astype("int16"))
+    with wave.open(os.path.join(REF, "TestFile16BitStereo.wav")) as w:
+        st = np.frombuffer(w.readframes(w.getnframes()), dtype=np.int16).reshape(-1, 2)[30000:30000 + 6 * 4096].T.copy()
+    outs = []
+    for row in st:                                                                             # Example2.py:13-22
+        d = ref.CreateLowCutFilter(800)
+        outs.append((_run_chunks(d, row.astype("float32") / 32768, 4096) * 32767).astype("int16"))
+    _save("lowcut800_c4096_stereo_int16", dict(kind="lowcut", fs=44100, chunk=4096, args=[800], numpy=numpy_version,
+                                                source="Example2.py chain, planar L/R rows"),
+          x=st, y=np.stack(outs))
+
     # --- tap designs (float64) so the host-side design code is pinned too --------------
     ref.config.initialize(44100, 4096)
     d = ref.CreateLowCutFilter(800)

@@ -215,6 +215,25 @@ def test_capi_rejects_bad_geometry(gpu_lib):
         assert gpu_lib.adt_last_error(ctx.h)
 
 
+# ---- 16-bit PCM mode ----------------------------------------------------
+@pytest.mark.parametrize("name", ["lowcut800_c4096_wav_int16", "lowcut800_c4096_stereo_int16"])
+def test_int16_mode_matches_reference_chain(gpu_lib, name):
+    """int16 in -> /32768 -> filter -> *32767 -> truncate, all fused.  The float path differs from the
+    reference by ~3e-7, so after truncation a sample may land one LSB away; never more."""
+    meta, arr = load_golden(name)
+    adt.config.initialize(meta["fs"], meta["chunk"])
+    rows = 1 if arr["x"].ndim == 1 else arr["x"].shape[0]
+    dev = adt.CreateLowCutFilter(*meta["args"], channels=rows)
+    y = dev.process_int16(arr["x"])
+    assert y.dtype == np.int16 and y.shape == arr["y"].shape
+    diff = np.abs(y.astype(np.int32) - arr["y"].astype(np.int32))
+    assert diff.max() <= 1
+    assert np.mean(diff != 0) < 0.05
+    # and it is exactly the float path with the two conversions applied around it
+    yf = dev.process(arr["x"].astype(np.float32) / 32768)
+    assert np.array_equal(y, (yf * 32767).astype(np.int16))
+
+
 # ---- the streaming biquad: bit-exact ---------------------------------------------
 @pytest.mark.parametrize("tag", ["f32", "f64"])
 def test_biquad_bit_exact(gpu_lib, tag):

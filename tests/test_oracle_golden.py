@@ -50,6 +50,19 @@ def test_closed_form_matches_reference(name):
     assert np.max(np.abs(y - arr["y"])) <= 1e-6
 
 
+@pytest.mark.parametrize("name", ["lowcut800_c4096_wav_int16", "lowcut800_c4096_stereo_int16"])
+def test_int16_chain_oracle(name):
+    meta, arr = load_golden(name)
+    x = np.atleast_2d(arr["x"]); want = np.atleast_2d(arr["y"])
+    for row, w in zip(x, want):
+        dev = oracle.SlidingFftFilter(meta["fs"], meta["chunk"], meta["args"][0], "lowcut")
+        c = meta["chunk"]
+        xf = row.astype("float32") / 32768                               # Utility.py:236-237
+        y = np.concatenate([dev.apply(xf[i:i + c]) for i in range(0, len(xf), c)])
+        got = (y * 32767).astype("int16")                                # Utility.py:306
+        assert np.max(np.abs(got.astype(int) - w.astype(int))) <= 1 and np.mean(got != w) < 0.01
+
+
 def test_mask_design_matches_reference():
     meta, arr = load_golden("masks_c4096")
     from oracle.fftfilter import _padded_mask
