@@ -184,6 +184,9 @@ extern "C" int adt_ctx_create(int device, adt_ctx** out) {
         const FirVariant* v = &vars[vi];
         for (fir_kernel_fn f : {v->cplx, v->real, v->cplx_i16, v->real_i16}) {
             e = cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->smem);
+            if (e == cudaSuccess && getenv("ADT_FIR_CARVEOUT"))  // tuning knob: % of the 228 KB given to shared memory
+                e = cudaFuncSetAttribute((const void*)f, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         atoi(getenv("ADT_FIR_CARVEOUT")));
             if (e != cudaSuccess) {
                 delete ctx;
                 return ADT_ERR_CUDA;

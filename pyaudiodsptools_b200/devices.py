@@ -57,14 +57,20 @@ class _FirDevice:
         self._h = h
 
     # -- streaming: one reference .apply() ---------------------------------
-    def apply(self, float32_array_input):
+    def apply(self, float32_array_input, out=None):
+        """One reference-style step.  For large batches pass arrays from ``dev.context.pinned_empty`` (and an
+        ``out=`` buffer of the same kind): page-locked buffers are DMA'd directly, pageable ones are staged."""
         # numpy.concatenate(axis=None) is what makes the reference accept lists / 2-D / int16 input
         flat = np.concatenate((float32_array_input,), axis=None)
         if flat.size != self.channels * self.chunk_size:
             raise ValueError(f"operands could not be broadcast together: expected {self.channels} x "
                              f"{self.chunk_size} samples, got {flat.size}")
         x = np.ascontiguousarray(flat, dtype=np.float32)
-        y = np.empty(self.channels * self.chunk_size, dtype=np.float32)
+        if out is None:
+            y = np.empty(self.channels * self.chunk_size, dtype=np.float32)
+        else:
+            assert out.dtype == np.float32 and out.size == flat.size and out.flags["C_CONTIGUOUS"]
+            y = out.reshape(-1)
         self._ctx.check(self._ctx.lib.adt_fir_apply_host(self._h, x.ctypes.data, y.ctypes.data))
         return y if self.channels == 1 else y.reshape(self.channels, self.chunk_size)
 
