@@ -52,22 +52,28 @@ __device__ __forceinline__ FirItem<E> fir_item(const FirKernelArgs& a, long long
     return it;
 }
 
-// Warm L2 with the window of the item `ahead` positions later in launch order (about one wave of
+// Warm L2 with the window of the item `ahead` positions later in launch order (about half a wave of
 // resident CTAs): by the time that CTA starts, its 64 loads per thread hit L2 instead of HBM.
+// One thread hands each row's window to the bulk-copy (TMA) engine as a single
+// cp.async.bulk.prefetch.L2 (SASS: UBLKPF) — no per-line prefetch instructions in the hot loop.
 template <int N, int T, class E>
 __device__ __forceinline__ void fir_prefetch_l2(const FirKernelArgs& a, long long item, int t) {
-    if (a.prefetch_ahead <= 0) return;
+    if (a.prefetch_ahead <= 0 || t >= 2) return;
     const long long nxt = item + a.prefetch_ahead;
     if (nxt >= a.n_items) return;
     const FirItem<E> it = fir_item<E>(a, nxt);
-    // 2 rows x N samples, one prefetch per 128-byte line
-    constexpr int PER_LINE = 128 / (int)sizeof(E);
-    constexpr int LINES = N / PER_LINE;
-    for (int l = t; l < 2 * LINES; l += T) {
-        const E* base = (l < LINES) ? it.xa : it.xb;
-        const long long s = it.ws + (long long)(l % LINES) * PER_LINE;
-        if (base && s >= 0 && s < a.g.n_in) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + s));
-    }
+    const E* base = t ? it.xb : it.xa;
+    if (!base) return;
+    // clamp the window to the valid samples and to 16-byte granularity
+    constexpr long long G = 16 / (long long)sizeof(E);
+    long long lo = it.ws < 0 ? 0 : it.ws, hi = it.ws + N;
+    if (hi > a.g.n_in) hi = a.g.n_in;
+    const unsigned long long addr = (unsigned long long)(base + lo);
+    const long long skip = (long long)((16 - (addr & 15)) & 15) / (long long)sizeof(E);   // up to the next 16-byte boundary
+    lo += skip;
+    const long long cnt = (hi - lo) / G * G;
+    if (cnt <= 0) return;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + lo), "r"((unsigned)(cnt * sizeof(E))) : "memory");
 }
 
 // One CTA per work item.  (A persistent CTA-loop over items was measured 15 % slower on B200 — with
