@@ -225,8 +225,8 @@ def main():
 
     dist = None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the one JSON line (no "NCCL version ..." banner)
         import torch
         import torch.distributed as dist_mod
         torch.cuda.set_device(local_rank)
