@@ -83,6 +83,7 @@ struct FirVariant {
     size_t smem;
     fir_kernel_fn cplx, real;
     fir_kernel_fn cplx_i16, real_i16;  // 16-bit PCM in/out (IoI16)
+    fir_kernel_fn persist_cplx, persist_real;  // persistent dynamic-queue variant (p32, float32 I/O) or null
     void (*build)(const float* mask, bool real_only, HostTables& out);
 };
 
@@ -98,6 +99,8 @@ FirVariant make_variant32(const char* name) {
     v.real = fir_block_kernel<C, float, MIN_CTAS>;
     v.cplx_i16 = fir_block_kernel<C, cf, MIN_CTAS, IoI16>;
     v.real_i16 = fir_block_kernel<C, float, MIN_CTAS, IoI16>;
+    v.persist_cplx = fir_persist_kernel<C, cf, MIN_CTAS>;
+    v.persist_real = fir_persist_kernel<C, float, MIN_CTAS>;
     v.build = [](const float* mask, bool real_only, HostTables& out) {
         out.tw1 = build_tw1<C>();
         out.tw2 = build_tw2<C>();
@@ -118,6 +121,7 @@ FirVariant make_variant16(const char* name) {
     v.real = fir16_block_kernel<C, float, MIN_CTAS>;
     v.cplx_i16 = fir16_block_kernel<C, cf, MIN_CTAS, IoI16>;
     v.real_i16 = fir16_block_kernel<C, float, MIN_CTAS, IoI16>;
+    v.persist_cplx = v.persist_real = nullptr;
     v.build = [](const float* mask, bool real_only, HostTables& out) {
         out.tw1 = build16_tw1<C>();
         out.tw2 = build16_tw2<C>();
@@ -182,7 +186,8 @@ extern "C" int adt_ctx_create(int device, adt_ctx** out) {
     const FirVariant* vars = all_variants(&n_var);
     for (int vi = 0; vi < n_var; ++vi) {
         const FirVariant* v = &vars[vi];
-        for (fir_kernel_fn f : {v->cplx, v->real, v->cplx_i16, v->real_i16}) {
+        for (fir_kernel_fn f : {v->cplx, v->real, v->cplx_i16, v->real_i16, v->persist_cplx, v->persist_real}) {
+            if (!f) continue;
             e = cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->smem);
             if (e == cudaSuccess && getenv("ADT_FIR_CARVEOUT"))  // tuning knob: % of the 228 KB given to shared memory
                 e = cudaFuncSetAttribute((const void*)f, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -339,6 +344,7 @@ struct adt_fir {
     cf* d_tw1 = nullptr;
     cf* d_tw2 = nullptr;
     // streaming state: two [n_channels][hist_pitch] buffers (history ++ newest chunk)
+    unsigned int* d_counter = nullptr;  // work queue head of the persistent variant
     int resident_ctas = 0;  // CTAs resident at once (SMs x CTAs per SM), computed on first launch
     float* d_hist[2] = {nullptr, nullptr};
     int cur = 0;
@@ -350,6 +356,8 @@ struct adt_fir {
     size_t in_cap[ADT_COPY_STREAMS] = {};
     size_t out_cap[ADT_COPY_STREAMS] = {};
 };
+
+__global__ void fir_set_counter(unsigned int* c, unsigned int v) { *c = v; }
 
 static int fir_launch(adt_fir* f, cudaStream_t s, const void* x, int64_t in_pitch, int64_t n_in, int64_t in_shift,
                       void* y, int64_t out_pitch, int64_t n_out, int32_t n_rows, bool i16 = false) {
@@ -390,7 +398,20 @@ static int fir_launch(adt_fir* f, cudaStream_t s, const void* x, int64_t in_pitc
     // L2 prefetch distance in units of one wave of resident CTAs (measured: flat between 0.25 and 1; 0 = off costs 9 %)
     const double pf = getenv("ADT_FIR_PREFETCH") ? atof(getenv("ADT_FIR_PREFETCH")) : 0.5;
     a.prefetch_ahead = (int)(pf * f->resident_ctas);
-    const unsigned grid = (unsigned)a.n_items;
+    unsigned grid = (unsigned)a.n_items;
+    a.work_counter = nullptr;
+    // persistent dynamic-queue variant: only worth it when there are several waves of items
+    static const int persist_mode = getenv("ADT_FIR_PERSIST") ? atoi(getenv("ADT_FIR_PERSIST")) : 0;
+    fir_kernel_fn kp = f->d.mask_is_real ? f->var->persist_real : f->var->persist_cplx;
+    if (persist_mode && !i16 && kp && a.n_items >= 4LL * f->resident_ctas) {
+        if (!f->d_counter) CK(ctx, cudaMalloc((void**)&f->d_counter, sizeof(unsigned int)));
+        grid = (unsigned)f->resident_ctas;
+        const unsigned int init = grid;
+        fir_set_counter<<<1, 1, 0, s>>>(f->d_counter, init);
+        ctx->launches++;
+        a.work_counter = f->d_counter;
+        k = kp;
+    }
     k<<<grid, f->var->threads, f->var->smem, s>>>(a);
     CK(ctx, cudaGetLastError());
     ctx->launches++;
@@ -403,6 +424,7 @@ extern "C" int adt_fir_destroy(adt_fir* f) {
     cudaDeviceSynchronize();
     cudaFree(f->d_mask);
     cudaFree(f->d_coef_x);
+    cudaFree(f->d_counter);
     cudaFree(f->d_tw1);
     cudaFree(f->d_tw2);
     cudaFree(f->d_hist[0]);

@@ -24,6 +24,7 @@ struct FirKernelArgs {
     int blocks_per_row;    // ceil(n_out / hop)
     long long n_items;     // blocks_per_row * ceil(n_rows / 2)
     int prefetch_ahead;    // L2-prefetch the window of item + prefetch_ahead (0 = off)
+    unsigned int* work_counter;  // persistent variant: next unclaimed item (preset to gridDim.x by the host)
     FirGeom g;
 };
 
@@ -76,8 +77,8 @@ __device__ __forceinline__ void fir_prefetch_l2(const FirKernelArgs& a, long lon
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + lo), "r"((unsigned)(cnt * sizeof(E))) : "memory");
 }
 
-// One CTA per work item.  (A persistent CTA-loop over items was measured 15 % slower on B200 — with
-// or without start skew — and is not used)
+// One CTA per work item (the default).  Persistent CTA loops were measured slower at N = 8192 on B200
+// (static stride -15 %, dynamic queue -5 %); see fir_persist_kernel below and DESIGN.md §5.4.
 template <class C, class MaskT, int MIN_CTAS, class IO = IoF32>
 __global__ void __launch_bounds__(C::T, MIN_CTAS) fir_block_kernel(const FirKernelArgs a) {
     typedef typename IO::elem E;
@@ -99,6 +100,40 @@ __global__ void __launch_bounds__(C::T, MIN_CTAS) fir_block_kernel(const FirKern
     __syncthreads();
     inv_stage1<C>(v, t, a.tw1, tile);
     store_slice<C, IO>(v, t, it.ya, it.yb, it.m0, a.g);
+}
+
+// PERSISTENT variant with a DYNAMIC work queue: the grid is one wave of resident CTAs; each CTA claims
+// items from an atomic counter (a static stride would pace the kernel by the slowest SM — measured 15 %
+// slower).  No barrier is needed between items because every tile exchange is in place, so warps flow
+// into the next item while slower warps of the CTA finish the current one, and there is no CTA
+// launch / drain gap.  The next item index is claimed before barrier 1 and read between the barriers.
+template <class C, class MaskT, int MIN_CTAS, class IO = IoF32>
+__global__ void __launch_bounds__(C::T, MIN_CTAS) fir_persist_kernel(const FirKernelArgs a) {
+    typedef typename IO::elem E;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cf* tile = reinterpret_cast<cf*>(smem_raw);
+    __shared__ unsigned int next_item_s;
+    const int t = threadIdx.x;
+    long long item = blockIdx.x;
+    while (item < a.n_items) {
+        const FirItem<E> it = fir_item<E>(a, item);
+        cf v[32];
+        load_window<C, IO>(v, t, it.xa, it.xb, it.ws, a.g.n_in);
+        fir_prefetch_l2<C::N, C::T, E>(a, item, t);
+        fwd_stage1<C>(v, t, a.tw1, tile);
+        if (t == 0) next_item_s = atomicAdd(a.work_counter, 1u);
+        __syncthreads();
+        fwd_stage2<C>(v, t, a.tw2, tile);
+        __syncwarp();
+        mid_stage3<C, MaskT>(v, t, reinterpret_cast<const MaskT*>(a.mask), tile);
+        __syncwarp();
+        inv_stage2<C>(v, t, a.tw2, tile);
+        const unsigned int next_item = next_item_s;
+        __syncthreads();
+        inv_stage1<C>(v, t, a.tw1, tile);
+        store_slice<C, IO>(v, t, it.ya, it.yb, it.m0, a.g);
+        item = next_item;
+    }
 }
 
 // 16 points per thread (fft_core16.cuh): 512 threads at <= 64 registers -> 32 warps per SM.
