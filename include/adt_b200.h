@@ -126,6 +126,26 @@ int adt_fir_apply_host(adt_fir* fir, const float* in_host, float* out_host);
 int adt_fir_apply_dev(adt_fir* fir, const float* in_dev, float* out_dev); /* async */
 int adt_fir_reset(adt_fir* fir);                                          /* history := 0 */
 
+/* ---- in-repo consumers of the path ------------------------------------------
+ * Pointwise wave-shapers, float32 arithmetic in the reference's operation order:
+ *   kind 1 = CreateSaturator.apply   (EffectSaturator.py:41-48)  params = {s, 1-s, (s+1)/2, gain, mode(1|2)}
+ *            with s = 10^(threshold_dB/20), gain = 10^(makeup_dB/20)                    (bit-exact)
+ *   kind 2 = CreateSoftClipper.apply (EffectSoftClipper.py:37-44) params = {drive+1, 0, 0, 0, 0}  (powf ulps)
+ * adt_fir_set_epilogue fuses one into the FIR kernel's store (kind 0 detaches). */
+int adt_fir_set_epilogue(adt_fir* fir, int kind, const float* params);
+int adt_shape_apply_dev(adt_ctx* ctx, int kind, const float* params, const float* x_dev, float* y_dev, int64_t n);
+int adt_shape_apply_host(adt_ctx* ctx, int kind, const float* params, const float* x_host, float* y_host, int64_t n);
+
+/* CreateDelay.apply (EffectDelay.py:31-74): y = x + sum_k ramp[k] * x[n - delay*(k+1)] accumulated in a
+ * float32 delay line in the reference's order (bit-exact); wet != 0 returns only the delay line.
+ * Buffers are [n_channels][n] contiguous, n <= 2*delay_samples per call. */
+typedef struct adt_delay adt_delay;
+int adt_delay_create(adt_ctx* ctx, int64_t delay_samples, int32_t feedback_loops, const float* ramp, int32_t wet,
+                     int32_t n_channels, adt_delay** out);
+int adt_delay_destroy(adt_delay* dl);
+int adt_delay_apply_dev(adt_delay* dl, const float* x_dev, float* y_dev, int64_t n);
+int adt_delay_apply_host(adt_delay* dl, const float* x_host, float* y_host, int64_t n);
+
 /* ---- the streaming biquad of CreateEQ3Band (EffectEQ3Band.py:90-180) -------
  * y[n] = c0*x[n-1] + c1*x[n-2] + c2*x[n-3] - c3*y[n-1] - c4*y[n-2]
  * (the reference's one-sample numerator delay is part of the contract),

@@ -16,3 +16,4 @@ from .fftfilter import (  # noqa: F401
     SlidingFftFilter, SlidingFftEq3, fir_stream_f64, stream_delay,
 )
 from .biquad import Eq3BandBiquad  # noqa: F401
+from .consumers import FeedbackDelay, saturator, soft_clipper  # noqa: F401

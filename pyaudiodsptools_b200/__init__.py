@@ -13,7 +13,8 @@ GPU raises ``AdtError``.
 from . import config  # noqa: F401
 from ._native import AdtError  # noqa: F401
 from .devices import CreateEQ3Band, CreateEQ3BandFFT, CreateHighCutFilter, CreateLowCutFilter  # noqa: F401
+from .consumers import CreateDelay, CreateSaturator, CreateSoftClipper  # noqa: F401
 from .utility import CombineChunks, MakeChunks  # noqa: F401
 
 __all__ = ["config", "CreateHighCutFilter", "CreateLowCutFilter", "CreateEQ3BandFFT", "CreateEQ3Band",
-           "MakeChunks", "CombineChunks", "AdtError"]
+           "CreateSaturator", "CreateSoftClipper", "CreateDelay", "MakeChunks", "CombineChunks", "AdtError"]

@@ -63,6 +63,13 @@ PROTOTYPES = {
     "adt_fir_apply_host": (C.c_int, [_P, _P, _P]),
     "adt_fir_apply_dev": (C.c_int, [_P, _P, _P]),
     "adt_fir_reset": (C.c_int, [_P]),
+    "adt_fir_set_epilogue": (C.c_int, [_P, C.c_int, _P]),
+    "adt_shape_apply_dev": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int64]),
+    "adt_shape_apply_host": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int64]),
+    "adt_delay_create": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "adt_delay_destroy": (C.c_int, [_P]),
+    "adt_delay_apply_dev": (C.c_int, [_P, _P, _P, C.c_int64]),
+    "adt_delay_apply_host": (C.c_int, [_P, _P, _P, C.c_int64]),
     "adt_biquad_create": (C.c_int, [_P, C.POINTER(C.c_double), C.c_int32, C.c_int32, C.POINTER(_P)]),
     "adt_biquad_destroy": (C.c_int, [_P]),
     "adt_biquad_reset": (C.c_int, [_P]),

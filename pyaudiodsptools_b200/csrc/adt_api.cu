@@ -84,6 +84,7 @@ struct FirVariant {
     fir_kernel_fn cplx, real;
     fir_kernel_fn cplx_i16, real_i16;  // 16-bit PCM in/out (IoI16)
     fir_kernel_fn persist_cplx, persist_real;  // persistent dynamic-queue variant (p32, float32 I/O) or null
+    fir_kernel_fn shaped_cplx, shaped_real;    // float32 I/O with the wave-shaper store epilogue
     void (*build)(const float* mask, bool real_only, HostTables& out);
 };
 
@@ -101,6 +102,8 @@ FirVariant make_variant32(const char* name) {
     v.real_i16 = fir_block_kernel<C, float, MIN_CTAS, IoI16>;
     v.persist_cplx = fir_persist_kernel<C, cf, MIN_CTAS>;
     v.persist_real = fir_persist_kernel<C, float, MIN_CTAS>;
+    v.shaped_cplx = fir_block_kernel<C, cf, MIN_CTAS, IoF32, true>;
+    v.shaped_real = fir_block_kernel<C, float, MIN_CTAS, IoF32, true>;
     v.build = [](const float* mask, bool real_only, HostTables& out) {
         out.tw1 = build_tw1<C>();
         out.tw2 = build_tw2<C>();
@@ -122,6 +125,8 @@ FirVariant make_variant16(const char* name) {
     v.cplx_i16 = fir16_block_kernel<C, cf, MIN_CTAS, IoI16>;
     v.real_i16 = fir16_block_kernel<C, float, MIN_CTAS, IoI16>;
     v.persist_cplx = v.persist_real = nullptr;
+    v.shaped_cplx = fir16_block_kernel<C, cf, MIN_CTAS, IoF32, true>;
+    v.shaped_real = fir16_block_kernel<C, float, MIN_CTAS, IoF32, true>;
     v.build = [](const float* mask, bool real_only, HostTables& out) {
         out.tw1 = build16_tw1<C>();
         out.tw2 = build16_tw2<C>();
@@ -132,12 +137,11 @@ FirVariant make_variant16(const char* name) {
 
 const FirVariant* all_variants(int* count) {
     static const FirVariant table[] = {
-        // default per size first; ADT_FIR_KERNEL=<name> overrides (A/B experiments)
+        make_variant32<FirCfg<16, 8>, 4>("p32"),   // N = 4096,  128 threads, 4 CTAs/SM
+        make_variant32<FirCfg<16, 16>, 2>("p32"),  // N = 8192,  256 threads, 2 CTAs/SM  (headline kernel)
+        make_variant32<FirCfg<16, 32>, 1>("p32"),  // N = 16384, 512 threads, 1 CTA/SM
         make_variant16<Fir16Cfg<16>, 4>("p16"),    // N = 4096,  256 threads, <= 64 regs
         make_variant16<Fir16Cfg<32>, 2>("p16"),    // N = 8192,  512 threads, <= 64 regs, 32 warps/SM
-        make_variant32<FirCfg<16, 32>, 1>("p32"),  // N = 16384, 512 threads, 128 regs
-        make_variant32<FirCfg<16, 8>, 4>("p32"),   // N = 4096,  128 threads
-        make_variant32<FirCfg<16, 16>, 2>("p32"),  // N = 8192,  256 threads, 128 regs
     };
     *count = (int)(sizeof table / sizeof table[0]);
     return table;
@@ -186,7 +190,8 @@ extern "C" int adt_ctx_create(int device, adt_ctx** out) {
     const FirVariant* vars = all_variants(&n_var);
     for (int vi = 0; vi < n_var; ++vi) {
         const FirVariant* v = &vars[vi];
-        for (fir_kernel_fn f : {v->cplx, v->real, v->cplx_i16, v->real_i16, v->persist_cplx, v->persist_real}) {
+        for (fir_kernel_fn f : {v->cplx, v->real, v->cplx_i16, v->real_i16, v->persist_cplx, v->persist_real,
+                                v->shaped_cplx, v->shaped_real}) {
             if (!f) continue;
             e = cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->smem);
             if (e == cudaSuccess && getenv("ADT_FIR_CARVEOUT"))  // tuning knob: % of the 228 KB given to shared memory
@@ -344,6 +349,7 @@ struct adt_fir {
     cf* d_tw1 = nullptr;
     cf* d_tw2 = nullptr;
     // streaming state: two [n_channels][hist_pitch] buffers (history ++ newest chunk)
+    FirShape shape{0, 0, 0.f, 0.f, 0.f, 0.f};  // store epilogue (adt_fir_set_epilogue)
     unsigned int* d_counter = nullptr;  // work queue head of the persistent variant
     int resident_ctas = 0;  // CTAs resident at once (SMs x CTAs per SM), computed on first launch
     float* d_hist[2] = {nullptr, nullptr};
@@ -385,8 +391,13 @@ static int fir_launch(adt_fir* f, cudaStream_t s, const void* x, int64_t in_pitc
     a.g.n_out = n_out;
     a.g.in_pitch = in_pitch;
     a.g.out_pitch = out_pitch;
-    fir_kernel_fn k = i16 ? (f->d.mask_is_real ? f->var->real_i16 : f->var->cplx_i16)
-                          : (f->d.mask_is_real ? f->var->real : f->var->cplx);
+    a.g.shape = f->shape;
+    const bool shaped = f->shape.kind != 0;
+    if (shaped && i16)
+        return adt_set_error(ctx, ADT_ERR_UNSUPPORTED, "the wave-shaper epilogue is built for float32 I/O only");
+    fir_kernel_fn k = shaped ? (f->d.mask_is_real ? f->var->shaped_real : f->var->shaped_cplx)
+                      : i16  ? (f->d.mask_is_real ? f->var->real_i16 : f->var->cplx_i16)
+                             : (f->d.mask_is_real ? f->var->real : f->var->cplx);
     if (a.n_items > 0x7fffffffLL)
         return adt_set_error(ctx, ADT_ERR_UNSUPPORTED, "too many work items: %lld", (long long)a.n_items);
     if (f->resident_ctas == 0) {  // CTAs in flight at once = how far ahead the L2 prefetch looks
@@ -403,7 +414,7 @@ static int fir_launch(adt_fir* f, cudaStream_t s, const void* x, int64_t in_pitc
     // persistent dynamic-queue variant: only worth it when there are several waves of items
     static const int persist_mode = getenv("ADT_FIR_PERSIST") ? atoi(getenv("ADT_FIR_PERSIST")) : 0;
     fir_kernel_fn kp = f->d.mask_is_real ? f->var->persist_real : f->var->persist_cplx;
-    if (persist_mode && !i16 && kp && a.n_items >= 4LL * f->resident_ctas) {
+    if (persist_mode && !i16 && !shaped && kp && a.n_items >= 4LL * f->resident_ctas) {
         if (!f->d_counter) CK(ctx, cudaMalloc((void**)&f->d_counter, sizeof(unsigned int)));
         grid = (unsigned)f->resident_ctas;
         const unsigned int init = grid;
@@ -441,10 +452,10 @@ extern "C" int adt_fir_destroy(adt_fir* f) {
 extern "C" int adt_fir_create(adt_ctx* ctx, const adt_fir_desc* desc, const float* mask, adt_fir** out) {
     if (!ctx || !desc || !mask || !out) return ADT_ERR_INVALID;
     *out = nullptr;
-    // Default kernel family (measured): "p32" (32 points/thread) everywhere except N = 4096
-    // with a real mask, where "p16" (16 points/thread) is marginally faster.  ADT_FIR_KERNEL overrides (A/B).
+    // Default kernel family (measured): "p32" (32 points/thread) for every size; "p16"
+    // (16 points/thread, 32 warps/SM) is kept as an A/B family.  ADT_FIR_KERNEL overrides.
     const char* want = getenv("ADT_FIR_KERNEL");
-    if (!want || !*want) want = (desc->fft_size == 4096 && desc->mask_is_real) ? "p16" : "p32";
+    if (!want || !*want) want = "p32";
     const FirVariant* var = find_variant(desc->fft_size, want);
     if (!var)
         return adt_set_error(ctx, ADT_ERR_UNSUPPORTED, "fft_size %d not in {4096, 8192, 16384}", desc->fft_size);
@@ -486,6 +497,21 @@ extern "C" int adt_fir_create(adt_ctx* ctx, const adt_fir_desc* desc, const floa
         return adt_cuda_fail(ctx, e, "adt_fir_create");
     }
     *out = f;
+    return ADT_OK;
+}
+
+// Attach (kind 1 saturator / 2 soft clipper) or detach (kind 0) a wave-shaper applied to every output
+// sample in the kernel's store phase.  params = {p0, p1, p2, p3, mode} as for adt_shape_apply_*.
+extern "C" int adt_fir_set_epilogue(adt_fir* f, int kind, const float* params) {
+    if (!f) return ADT_ERR_INVALID;
+    if (kind == 0) {
+        f->shape = FirShape{0, 0, 0.f, 0.f, 0.f, 0.f};
+        return ADT_OK;
+    }
+    if (kind < 1 || kind > 2 || !params) return adt_set_error(f->ctx, ADT_ERR_INVALID, "bad epilogue kind %d", kind);
+    const int mode = kind == 1 ? (int)params[4] : 0;
+    if (kind == 1 && mode != 1 && mode != 2) return adt_set_error(f->ctx, ADT_ERR_INVALID, "saturator mode must be 1 or 2");
+    f->shape = FirShape{kind, mode, params[0], params[1], params[2], params[3]};
     return ADT_OK;
 }
 
@@ -549,7 +575,8 @@ static int fir_process_host_impl(adt_fir* f, const void* xv, int64_t in_pitch, i
     char* y = static_cast<char*>(yv);
     // row groups of ~48 MB, an even number of rows (channel pairs stay together); pitches keep 128-byte rows
     const int64_t din_pitch = (n_in + 63) / 64 * 64, dout_pitch = (n_out + 63) / 64 * 64;
-    int64_t g_rows = (int64_t)(48u << 20) / (int64_t)((din_pitch > dout_pitch ? din_pitch : dout_pitch) * es);
+    static const int64_t group_mb = getenv("ADT_FIR_GROUP_MB") ? atoi(getenv("ADT_FIR_GROUP_MB")) : 48;  // tuning knob
+    int64_t g_rows = (group_mb << 20) / (int64_t)((din_pitch > dout_pitch ? din_pitch : dout_pitch) * es);
     g_rows = g_rows < 2 ? 2 : (g_rows & ~1LL);
     if (g_rows > n_rows) g_rows = (n_rows + 1) & ~1LL;
     // everything queued on the context stream so far must be done before the copy streams start

@@ -328,6 +328,11 @@ struct FirCfg {
 };
 
 // What one FIR block needs to know (see DESIGN.md §3 for the derivation).
+struct FirShape {   // store epilogue (shape.cuh ShapeParams); kind 0 = none
+    int kind, mode;
+    float p0, p1, p2, p3;
+};
+
 struct FirGeom {
     int hop;         // outputs produced per block
     int n0;          // first kept index of the N-point circular result
@@ -336,6 +341,7 @@ struct FirGeom {
     long long n_in;  // valid input samples per row (others read as 0)
     long long n_out; // outputs wanted per row
     long long in_pitch, out_pitch;  // row pitches in floats
+    FirShape shape;                 // pointwise wave-shaper applied to every output sample before the store
 };
 
 // Sample formats at the HBM boundary.  F32: the reference's float32 chunks.  I16: 16-bit PCM fused
@@ -487,13 +493,16 @@ ADT_HD void inv_stage1(cf* v, int t, const cf* __restrict__ tw1, const cf* tile)
     });
 }
 
+// store epilogue: identity unless a wave-shaper was attached (uniform branch; shape.cuh has the formulas)
+ADT_HD float fir_shape(const FirShape& sh, float v);
+
 // ---- phase 6: registers -> global (only the valid slice) -------------------
 // z[n], n = n1*M1 + t + u*T, goes to y[m0 + n - n0] when 0 <= n - n0 < hop and
 // the stream index is below n_out.  `lim` = min(hop, n_out - m0) folds both
 // upper bounds into one unsigned compare per element.
-template <class C, class IO = IoF32>
-ADT_HD void store_slice(const cf* v, int t, typename IO::elem* __restrict__ ya, typename IO::elem* __restrict__ yb,
-                        long long m0, const FirGeom& g) {
+template <class C, class IO, bool SHAPED>
+ADT_HD void store_slice_impl(const cf* v, int t, typename IO::elem* __restrict__ ya, typename IO::elem* __restrict__ yb,
+                             long long m0, const FirGeom& g) {
     const long long room = g.n_out - m0;
     const unsigned lim = (unsigned)(room < (long long)g.hop ? (room < 0 ? 0 : room) : g.hop);
     typename IO::elem* pa = ya + (m0 - g.n0) + t;
@@ -505,10 +514,17 @@ ADT_HD void store_slice(const cf* v, int t, typename IO::elem* __restrict__ ya, 
             constexpr int off = n1 * C::M1 + u * C::T;
             const cf z = v[u * C::N1 + brev<C::N1>(n1)];
             const bool ok = (unsigned)(jt + off) < lim;
-            if (ok) IO::store(pa + off, z.x);
-            if (ok && pb) IO::store(pb + off, z.y);
+            if (ok) IO::store(pa + off, (SHAPED ? fir_shape(g.shape, z.x) : z.x));
+            if (ok && pb) IO::store(pb + off, (SHAPED ? fir_shape(g.shape, z.y) : z.y));
         });
     });
+}
+
+// SHAPED kernels are separate instantiations, so the default kernels carry no epilogue code at all.
+template <class C, class IO = IoF32, bool SHAPED = false>
+ADT_HD void store_slice(const cf* v, int t, typename IO::elem* __restrict__ ya, typename IO::elem* __restrict__ yb,
+                        long long m0, const FirGeom& g) {
+    store_slice_impl<C, IO, SHAPED>(v, t, ya, yb, m0, g);
 }
 
 }  // namespace adt

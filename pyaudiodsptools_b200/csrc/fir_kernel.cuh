@@ -10,8 +10,16 @@
 
 #include "fft_core.cuh"
 #include "fft_core16.cuh"
+#include "shape.cuh"
 
 namespace adt {
+
+ADT_HD float fir_shape(const FirShape& sh, float v) {
+    if (sh.kind == 0) return v;
+    ShapeParams sp;
+    sp.kind = sh.kind; sp.mode = sh.mode; sp.p0 = sh.p0; sp.p1 = sh.p1; sp.p2 = sh.p2; sp.p3 = sh.p3;
+    return shape_apply(sp, v);
+}
 
 struct FirKernelArgs {
     const void* x;         // [n_rows][in_pitch]  float32 (IoF32) or int16 (IoI16)
@@ -79,7 +87,7 @@ __device__ __forceinline__ void fir_prefetch_l2(const FirKernelArgs& a, long lon
 
 // One CTA per work item (the default).  Persistent CTA loops were measured slower at N = 8192 on B200
 // (static stride -15 %, dynamic queue -5 %); see fir_persist_kernel below and DESIGN.md §5.4.
-template <class C, class MaskT, int MIN_CTAS, class IO = IoF32>
+template <class C, class MaskT, int MIN_CTAS, class IO = IoF32, bool SHAPED = false>
 __global__ void __launch_bounds__(C::T, MIN_CTAS) fir_block_kernel(const FirKernelArgs a) {
     typedef typename IO::elem E;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -99,7 +107,7 @@ __global__ void __launch_bounds__(C::T, MIN_CTAS) fir_block_kernel(const FirKern
     inv_stage2<C>(v, t, a.tw2, tile);
     __syncthreads();
     inv_stage1<C>(v, t, a.tw1, tile);
-    store_slice<C, IO>(v, t, it.ya, it.yb, it.m0, a.g);
+    store_slice<C, IO, SHAPED>(v, t, it.ya, it.yb, it.m0, a.g);
 }
 
 // PERSISTENT variant with a DYNAMIC work queue: the grid is one wave of resident CTAs; each CTA claims
@@ -137,7 +145,7 @@ __global__ void __launch_bounds__(C::T, MIN_CTAS) fir_persist_kernel(const FirKe
 }
 
 // 16 points per thread (fft_core16.cuh): 512 threads at <= 64 registers -> 32 warps per SM.
-template <class C, class MaskT, int MIN_CTAS, class IO = IoF32>
+template <class C, class MaskT, int MIN_CTAS, class IO = IoF32, bool SHAPED = false>
 __global__ void __launch_bounds__(C::T, MIN_CTAS) fir16_block_kernel(const FirKernelArgs a) {
     typedef typename IO::elem E;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -157,7 +165,7 @@ __global__ void __launch_bounds__(C::T, MIN_CTAS) fir16_block_kernel(const FirKe
     inv16_stage2<C>(v, t, a.tw2, tile);
     __syncthreads();
     inv16_stage1<C>(v, t, a.tw1, tile);
-    store_slice16<C, IO>(v, t, it.ya, it.yb, it.m0, a.g);
+    store_slice16<C, IO, SHAPED>(v, t, it.ya, it.yb, it.m0, a.g);
 }
 
 }  // namespace adt

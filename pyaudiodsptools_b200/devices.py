@@ -41,7 +41,7 @@ def _snapshot_config():
 class _FirDevice:
     """Shared engine: composite taps -> block plan -> adt_fir."""
 
-    def __init__(self, taps, chunk, channels=1, device=0, fft_size=None):
+    def __init__(self, taps, chunk, channels=1, device=0, fft_size=None, epilogue=None):
         if channels < 1:
             raise ValueError("channels must be >= 1")
         self.chunk_size = chunk
@@ -55,6 +55,17 @@ class _FirDevice:
         h = C.c_void_p()
         self._ctx.check(self._ctx.lib.adt_fir_create(self._ctx.h, C.byref(desc), mask.ctypes.data, C.byref(h)))
         self._h = h
+        self.set_epilogue(epilogue)
+
+    def set_epilogue(self, shaper=None):
+        """Fuse a wave-shaper (consumers.CreateSaturator / CreateSoftClipper) into the kernel's store, or
+        detach it with None: every output sample y becomes shaper.apply(y) with no extra pass over HBM."""
+        if shaper is None:
+            self._ctx.check(self._ctx.lib.adt_fir_set_epilogue(self._h, 0, None))
+        else:
+            p = shaper._params()
+            self._ctx.check(self._ctx.lib.adt_fir_set_epilogue(self._h, shaper.kind, p.ctypes.data))
+        self.epilogue = shaper
 
     # -- streaming: one reference .apply() ---------------------------------
     def apply(self, float32_array_input, out=None):
@@ -140,22 +151,24 @@ class CreateHighCutFilter(_FirDevice):
     """FFT high-cut (low-pass) filter; latency = config.chunk_size.
     Reference: pyAudioDspTools/EffectFFTFilter.py:18-75."""
 
-    def __init__(self, cutoff_frequency=8000, channels=1, device=0, fft_size=None):
+    def __init__(self, cutoff_frequency=8000, channels=1, device=0, fft_size=None, epilogue=None):
         self.fS, chunk = _snapshot_config()
         self.fH = cutoff_frequency
         self.filter_length = design.filter_length(chunk)
-        super().__init__(design.highcut_taps(self.fS, chunk, cutoff_frequency), chunk, channels, device, fft_size)
+        super().__init__(design.highcut_taps(self.fS, chunk, cutoff_frequency), chunk, channels, device, fft_size,
+                         epilogue)
 
 
 class CreateLowCutFilter(_FirDevice):
     """FFT low-cut (high-pass) filter; latency = config.chunk_size.
     Reference: pyAudioDspTools/EffectFFTFilter.py:91-151."""
 
-    def __init__(self, cutoff_frequency=160, channels=1, device=0, fft_size=None):
+    def __init__(self, cutoff_frequency=160, channels=1, device=0, fft_size=None, epilogue=None):
         self.fS, chunk = _snapshot_config()
         self.fH = cutoff_frequency
         self.filter_length = design.filter_length(chunk)
-        super().__init__(design.lowcut_taps(self.fS, chunk, cutoff_frequency), chunk, channels, device, fft_size)
+        super().__init__(design.lowcut_taps(self.fS, chunk, cutoff_frequency), chunk, channels, device, fft_size,
+                         epilogue)
 
 
 class CreateEQ3BandFFT(_FirDevice):
@@ -164,7 +177,7 @@ class CreateEQ3BandFFT(_FirDevice):
     inverse FFTs + dry mix are one composite mask here."""
 
     def __init__(self, lowshelf_frequency, lowshelf_db, midband_frequency, midband_db, highshelf_frequency,
-                 highshelf_db, channels=1, device=0, fft_size=None):
+                 highshelf_db, channels=1, device=0, fft_size=None, epilogue=None):
         self.fS, chunk = _snapshot_config()
         self.fH_lowshelf, self.lowshelf_db = lowshelf_frequency, lowshelf_db
         self.fH_midband, self.midband_db = midband_frequency, midband_db
@@ -172,7 +185,7 @@ class CreateEQ3BandFFT(_FirDevice):
         self.filter_length = design.filter_length(chunk)
         taps = design.eq3_taps(self.fS, chunk, lowshelf_frequency, lowshelf_db, midband_frequency, midband_db,
                                highshelf_frequency, highshelf_db)
-        super().__init__(taps, chunk, channels, device, fft_size)
+        super().__init__(taps, chunk, channels, device, fft_size, epilogue)
 
 
 # ---------------------------------------------------------------------------

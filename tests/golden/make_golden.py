@@ -126,6 +126,24 @@ def main():
                                                 source="Example2.py chain, planar L/R rows"),
           x=st, y=np.stack(outs))
 
+    # --- the in-repo consumers of the path: wave-shapers and the delay ------------
+    xs = (np.random.default_rng(55).uniform(-1.3, 1.3, 4096)).astype("float32")    # incl. |x| > 1
+    for tag, kw in (("default", {}), ("soft", dict(saturation_threshold_in_db=-12.0, makeup_gain=0.0, mode="soft"))):
+        dev = ref.CreateSaturator(**kw)
+        _save(f"saturator_{tag}", dict(kind="saturator", kwargs=kw, numpy=numpy_version,
+                                       source="EffectSaturator.py:18-49"), x=xs, y=dev.apply(xs.copy()))
+    for tag, kw in (("default", {}), ("drive2", dict(drive=2.0))):
+        dev = ref.CreateSoftClipper(**kw)
+        _save(f"softclipper_{tag}", dict(kind="softclipper", kwargs=kw, numpy=numpy_version,
+                                         source="EffectSoftClipper.py:19-44"), x=xs, y=dev.apply(xs.copy()))
+    ref.config.initialize(44100, 512)
+    xd = _noise(91, 40 * 512)
+    for tag, kw in (("default", dict(time_in_ms=50)), ("wet3", dict(time_in_ms=20, feedback_loops=3, wet=True))):
+        dev = ref.CreateDelay(**kw)
+        y = np.concatenate([np.array(dev.apply(xd[i:i + 512].copy())) for i in range(0, len(xd), 512)])
+        _save(f"delay_{tag}", dict(kind="delay", fs=44100, chunk=512, kwargs=kw, numpy=numpy_version,
+                                   source="EffectDelay.py:31-74"), x=xd, y=y.astype("float32"))
+
     # --- tap designs (float64) so the host-side design code is pinned too --------------
     ref.config.initialize(44100, 4096)
     d = ref.CreateLowCutFilter(800)

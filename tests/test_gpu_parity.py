@@ -234,6 +234,61 @@ def test_int16_mode_matches_reference_chain(gpu_lib, name):
     assert np.array_equal(y, (yf * 32767).astype(np.int16))
 
 
+# ---- in-repo consumers of the path -------------------------------------------
+@pytest.mark.parametrize("name", ["saturator_default", "saturator_soft", "softclipper_default", "softclipper_drive2"])
+def test_shapers_match_reference(gpu_lib, name):
+    meta, arr = load_golden(name)
+    dev = (adt.CreateSaturator if meta["kind"] == "saturator" else adt.CreateSoftClipper)(**meta["kwargs"])
+    y = dev.apply(arr["x"])
+    assert y.dtype == np.float32
+    if meta["kind"] == "saturator":
+        np.testing.assert_array_equal(y, arr["y"])                  # same float32 operations in the same order
+    else:
+        assert np.max(np.abs(y - arr["y"])) <= 4e-7                 # powf: last-ulp differences only
+
+
+@pytest.mark.parametrize("name", ["delay_default", "delay_wet3"])
+def test_delay_bit_exact(gpu_lib, name):
+    meta, arr = load_golden(name)
+    adt.config.initialize(meta["fs"], meta["chunk"])
+    dev = adt.CreateDelay(**meta["kwargs"])
+    c = meta["chunk"]
+    y = np.concatenate([dev.apply(arr["x"][i:i + c]) for i in range(0, len(arr["x"]), c)])
+    np.testing.assert_array_equal(y, arr["y"])
+
+
+def test_delay_batched_with_prefilters(gpu_lib):
+    # pre-filter flags raise AttributeError in the reference (EffectDelay.py:56,58); here they compose
+    fs, c, ch = 44100, 512, 3
+    adt.config.initialize(fs, c)
+    dev = adt.CreateDelay(time_in_ms=30, feedback_loops=2, lowcut_filter_frequency=300, use_lowcut_filter=True,
+                          channels=ch)
+    lc = adt.CreateLowCutFilter(300, channels=ch)
+    x = np.random.default_rng(2).uniform(-1, 1, (ch, 12 * c)).astype(np.float32)
+    got = np.concatenate([dev.apply(x[:, i:i + c]) for i in range(0, 12 * c, c)], axis=1)
+    filt_all = lc.process(x)                                      # same filter, whole-buffer mode
+    for k in range(ch):
+        o = oracle.FeedbackDelay(fs, time_in_ms=30, feedback_loops=2)
+        want = np.concatenate([o.apply(filt_all[k, i:i + c]) for i in range(0, 12 * c, c)])
+        assert rms(got[k] - want) <= 2e-6
+
+
+def test_fused_epilogue_equals_separate_pass(gpu_lib):
+    fs, c = 44100, 4096
+    adt.config.initialize(fs, c)
+    x = np.random.default_rng(6).uniform(-1, 1, (5, 4 * c + 77)).astype(np.float32)
+    for shaper in (adt.CreateSaturator(-12.0, 1.0, 'soft'), adt.CreateSoftClipper(0.8)):
+        plain = adt.CreateHighCutFilter(6000, channels=5)
+        fused = adt.CreateHighCutFilter(6000, channels=5, epilogue=shaper)
+        y = plain.process(x)
+        assert np.array_equal(fused.process(x), shaper.apply(y))           # identical: same kernel, same formula
+        ys = np.concatenate([fused.apply(np.pad(x, ((0, 0), (0, 5 * c - x.shape[1])))[:, i:i + c])
+                             for i in range(0, 5 * c, c)], axis=1)
+        assert rms(ys - shaper.apply(y)) <= 1e-6
+        fused.set_epilogue(None)
+        assert np.array_equal(fused.process(x), y)
+
+
 # ---- the streaming biquad: bit-exact ---------------------------------------------
 @pytest.mark.parametrize("tag", ["f32", "f64"])
 def test_biquad_bit_exact(gpu_lib, tag):

@@ -63,6 +63,27 @@ def test_int16_chain_oracle(name):
         assert np.max(np.abs(got.astype(int) - w.astype(int))) <= 1 and np.mean(got != w) < 0.01
 
 
+@pytest.mark.parametrize("name", ["saturator_default", "saturator_soft", "softclipper_default", "softclipper_drive2"])
+def test_shaper_oracle_bit_exact(name):
+    meta, arr = load_golden(name)
+    fn = oracle.saturator if meta["kind"] == "saturator" else oracle.soft_clipper
+    kw = dict(meta["kwargs"])
+    if "saturation_threshold_in_db" in kw:
+        kw["threshold_db"] = kw.pop("saturation_threshold_in_db")
+    y = fn(arr["x"], **kw)
+    assert y.dtype == arr["y"].dtype
+    np.testing.assert_array_equal(y, arr["y"])
+
+
+@pytest.mark.parametrize("name", ["delay_default", "delay_wet3"])
+def test_delay_oracle_bit_exact(name):
+    meta, arr = load_golden(name)
+    dev = oracle.FeedbackDelay(meta["fs"], **meta["kwargs"])
+    c = meta["chunk"]
+    y = np.concatenate([dev.apply(arr["x"][i:i + c]) for i in range(0, len(arr["x"]), c)])
+    np.testing.assert_array_equal(y, arr["y"])
+
+
 def test_mask_design_matches_reference():
     meta, arr = load_golden("masks_c4096")
     from oracle.fftfilter import _padded_mask
