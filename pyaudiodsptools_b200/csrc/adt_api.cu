@@ -412,7 +412,8 @@ static int fir_launch(adt_fir* f, cudaStream_t s, const void* x, int64_t in_pitc
     unsigned grid = (unsigned)a.n_items;
     a.work_counter = nullptr;
     // persistent dynamic-queue variant: only worth it when there are several waves of items
-    static const int persist_mode = getenv("ADT_FIR_PERSIST") ? atoi(getenv("ADT_FIR_PERSIST")) : 0;
+    // measured: +1.5 % for the 1-CTA/SM N = 16384 kernel, -5 % for N = 8192 -> default on for 16384 only
+    const int persist_mode = getenv("ADT_FIR_PERSIST") ? atoi(getenv("ADT_FIR_PERSIST")) : (f->d.fft_size == 16384);
     fir_kernel_fn kp = f->d.mask_is_real ? f->var->persist_real : f->var->persist_cplx;
     if (persist_mode && !i16 && !shaped && kp && a.n_items >= 4LL * f->resident_ctas) {
         if (!f->d_counter) CK(ctx, cudaMalloc((void**)&f->d_counter, sizeof(unsigned int)));
