@@ -70,7 +70,7 @@ extern "C" int adt_device_count(int* count) {
 // ---------------------------------------------------------------------------
 namespace {
 
-typedef void (*fir_kernel_fn)(const FirKernelArgs);
+typedef void (*fir_kernel_fn)(const FirKernelArgs, const FirExtra);
 
 struct HostTables {
     std::vector<cf> tw1, tw2;
@@ -391,7 +391,9 @@ static int fir_launch(adt_fir* f, cudaStream_t s, const void* x, int64_t in_pitc
     a.g.n_out = n_out;
     a.g.in_pitch = in_pitch;
     a.g.out_pitch = out_pitch;
-    a.g.shape = f->shape;
+    FirExtra ex;
+    ex.work_counter = nullptr;
+    ex.shape = f->shape;
     const bool shaped = f->shape.kind != 0;
     if (shaped && i16)
         return adt_set_error(ctx, ADT_ERR_UNSUPPORTED, "the wave-shaper epilogue is built for float32 I/O only");
@@ -410,7 +412,6 @@ static int fir_launch(adt_fir* f, cudaStream_t s, const void* x, int64_t in_pitc
     const double pf = getenv("ADT_FIR_PREFETCH") ? atof(getenv("ADT_FIR_PREFETCH")) : 0.5;
     a.prefetch_ahead = (int)(pf * f->resident_ctas);
     unsigned grid = (unsigned)a.n_items;
-    a.work_counter = nullptr;
     // persistent dynamic-queue variant: only worth it when there are several waves of items
     // measured: +1.5 % for the 1-CTA/SM N = 16384 kernel, -5 % for N = 8192 -> default on for 16384 only
     const int persist_mode = getenv("ADT_FIR_PERSIST") ? atoi(getenv("ADT_FIR_PERSIST")) : (f->d.fft_size == 16384);
@@ -421,10 +422,10 @@ static int fir_launch(adt_fir* f, cudaStream_t s, const void* x, int64_t in_pitc
         const unsigned int init = grid;
         fir_set_counter<<<1, 1, 0, s>>>(f->d_counter, init);
         ctx->launches++;
-        a.work_counter = f->d_counter;
+        ex.work_counter = f->d_counter;
         k = kp;
     }
-    k<<<grid, f->var->threads, f->var->smem, s>>>(a);
+    k<<<grid, f->var->threads, f->var->smem, s>>>(a, ex);
     CK(ctx, cudaGetLastError());
     ctx->launches++;
     return ADT_OK;

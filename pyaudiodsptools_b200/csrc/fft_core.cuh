@@ -341,7 +341,6 @@ struct FirGeom {
     long long n_in;  // valid input samples per row (others read as 0)
     long long n_out; // outputs wanted per row
     long long in_pitch, out_pitch;  // row pitches in floats
-    FirShape shape;                 // pointwise wave-shaper applied to every output sample before the store
 };
 
 // Sample formats at the HBM boundary.  F32: the reference's float32 chunks.  I16: 16-bit PCM fused
@@ -502,7 +501,7 @@ ADT_HD float fir_shape(const FirShape& sh, float v);
 // upper bounds into one unsigned compare per element.
 template <class C, class IO, bool SHAPED>
 ADT_HD void store_slice_impl(const cf* v, int t, typename IO::elem* __restrict__ ya, typename IO::elem* __restrict__ yb,
-                             long long m0, const FirGeom& g) {
+                             long long m0, const FirGeom& g, const FirShape& shape) {
     const long long room = g.n_out - m0;
     const unsigned lim = (unsigned)(room < (long long)g.hop ? (room < 0 ? 0 : room) : g.hop);
     typename IO::elem* pa = ya + (m0 - g.n0) + t;
@@ -514,8 +513,8 @@ ADT_HD void store_slice_impl(const cf* v, int t, typename IO::elem* __restrict__
             constexpr int off = n1 * C::M1 + u * C::T;
             const cf z = v[u * C::N1 + brev<C::N1>(n1)];
             const bool ok = (unsigned)(jt + off) < lim;
-            if (ok) IO::store(pa + off, (SHAPED ? fir_shape(g.shape, z.x) : z.x));
-            if (ok && pb) IO::store(pb + off, (SHAPED ? fir_shape(g.shape, z.y) : z.y));
+            if (ok) IO::store(pa + off, (SHAPED ? fir_shape(shape, z.x) : z.x));
+            if (ok && pb) IO::store(pb + off, (SHAPED ? fir_shape(shape, z.y) : z.y));
         });
     });
 }
@@ -523,8 +522,8 @@ ADT_HD void store_slice_impl(const cf* v, int t, typename IO::elem* __restrict__
 // SHAPED kernels are separate instantiations, so the default kernels carry no epilogue code at all.
 template <class C, class IO = IoF32, bool SHAPED = false>
 ADT_HD void store_slice(const cf* v, int t, typename IO::elem* __restrict__ ya, typename IO::elem* __restrict__ yb,
-                        long long m0, const FirGeom& g) {
-    store_slice_impl<C, IO, SHAPED>(v, t, ya, yb, m0, g);
+                        long long m0, const FirGeom& g, const FirShape& shape) {
+    store_slice_impl<C, IO, SHAPED>(v, t, ya, yb, m0, g, shape);
 }
 
 }  // namespace adt

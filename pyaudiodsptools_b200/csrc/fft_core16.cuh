@@ -155,7 +155,8 @@ ADT_HD void inv16_stage1(cf* v, int t, const cf* __restrict__ tw1, const cf* til
 
 template <class C, class IO, bool SHAPED>
 ADT_HD void store_slice16_impl(const cf* v, int t, typename IO::elem* __restrict__ ya,
-                               typename IO::elem* __restrict__ yb, long long m0, const FirGeom& g) {
+                               typename IO::elem* __restrict__ yb, long long m0, const FirGeom& g,
+                               const FirShape& shape) {
     const long long room = g.n_out - m0;
     const unsigned lim = (unsigned)(room < (long long)g.hop ? (room < 0 ? 0 : room) : g.hop);
     typename IO::elem* pa = ya + (m0 - g.n0) + t;
@@ -166,15 +167,15 @@ ADT_HD void store_slice16_impl(const cf* v, int t, typename IO::elem* __restrict
         constexpr int off = n1 * C::M1;
         const cf z = v[brev<16>(n1)];
         const bool ok = (unsigned)(jt + off) < lim;
-        if (ok) IO::store(pa + off, (SHAPED ? fir_shape(g.shape, z.x) : z.x));
-        if (ok && pb) IO::store(pb + off, (SHAPED ? fir_shape(g.shape, z.y) : z.y));
+        if (ok) IO::store(pa + off, (SHAPED ? fir_shape(shape, z.x) : z.x));
+        if (ok && pb) IO::store(pb + off, (SHAPED ? fir_shape(shape, z.y) : z.y));
     });
 }
 
 template <class C, class IO = IoF32, bool SHAPED = false>
 ADT_HD void store_slice16(const cf* v, int t, typename IO::elem* __restrict__ ya, typename IO::elem* __restrict__ yb,
-                          long long m0, const FirGeom& g) {
-    store_slice16_impl<C, IO, SHAPED>(v, t, ya, yb, m0, g);
+                          long long m0, const FirGeom& g, const FirShape& shape) {
+    store_slice16_impl<C, IO, SHAPED>(v, t, ya, yb, m0, g, shape);
 }
 
 }  // namespace adt

@@ -32,8 +32,14 @@ struct FirKernelArgs {
     int blocks_per_row;    // ceil(n_out / hop)
     long long n_items;     // blocks_per_row * ceil(n_rows / 2)
     int prefetch_ahead;    // L2-prefetch the window of item + prefetch_ahead (0 = off)
-    unsigned int* work_counter;  // persistent variant: next unclaimed item (preset to gridDim.x by the host)
     FirGeom g;
+};
+
+// Rarely used extras travel in a SECOND kernel parameter: growing FirKernelArgs itself by even one
+// pointer makes nvcc 12.9 emit a different (measured 4 % slower) code shape for the default kernels.
+struct FirExtra {
+    unsigned int* work_counter;  // persistent variant: next unclaimed item (preset to gridDim.x by the host)
+    FirShape shape;              // SHAPED kernels: wave-shaper applied to every output sample before the store
 };
 
 // Work item -> (time block, channel pair).  Time block is the fast index so CTAs that run
@@ -88,7 +94,7 @@ __device__ __forceinline__ void fir_prefetch_l2(const FirKernelArgs& a, long lon
 // One CTA per work item (the default).  Persistent CTA loops were measured slower at N = 8192 on B200
 // (static stride -15 %, dynamic queue -5 %); see fir_persist_kernel below and DESIGN.md §5.4.
 template <class C, class MaskT, int MIN_CTAS, class IO = IoF32, bool SHAPED = false>
-__global__ void __launch_bounds__(C::T, MIN_CTAS) fir_block_kernel(const FirKernelArgs a) {
+__global__ void __launch_bounds__(C::T, MIN_CTAS) fir_block_kernel(const FirKernelArgs a, const FirExtra ex) {
     typedef typename IO::elem E;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cf* tile = reinterpret_cast<cf*>(smem_raw);
@@ -107,7 +113,7 @@ __global__ void __launch_bounds__(C::T, MIN_CTAS) fir_block_kernel(const FirKern
     inv_stage2<C>(v, t, a.tw2, tile);
     __syncthreads();
     inv_stage1<C>(v, t, a.tw1, tile);
-    store_slice<C, IO, SHAPED>(v, t, it.ya, it.yb, it.m0, a.g);
+    store_slice<C, IO, SHAPED>(v, t, it.ya, it.yb, it.m0, a.g, ex.shape);
 }
 
 // PERSISTENT variant with a DYNAMIC work queue: the grid is one wave of resident CTAs; each CTA claims
@@ -116,7 +122,7 @@ __global__ void __launch_bounds__(C::T, MIN_CTAS) fir_block_kernel(const FirKern
 // into the next item while slower warps of the CTA finish the current one, and there is no CTA
 // launch / drain gap.  The next item index is claimed before barrier 1 and read between the barriers.
 template <class C, class MaskT, int MIN_CTAS, class IO = IoF32>
-__global__ void __launch_bounds__(C::T, MIN_CTAS) fir_persist_kernel(const FirKernelArgs a) {
+__global__ void __launch_bounds__(C::T, MIN_CTAS) fir_persist_kernel(const FirKernelArgs a, const FirExtra ex) {
     typedef typename IO::elem E;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cf* tile = reinterpret_cast<cf*>(smem_raw);
@@ -129,7 +135,7 @@ __global__ void __launch_bounds__(C::T, MIN_CTAS) fir_persist_kernel(const FirKe
         load_window<C, IO>(v, t, it.xa, it.xb, it.ws, a.g.n_in);
         fir_prefetch_l2<C::N, C::T, E>(a, item, t);
         fwd_stage1<C>(v, t, a.tw1, tile);
-        if (t == 0) next_item_s = atomicAdd(a.work_counter, 1u);
+        if (t == 0) next_item_s = atomicAdd(ex.work_counter, 1u);
         __syncthreads();
         fwd_stage2<C>(v, t, a.tw2, tile);
         __syncwarp();
@@ -139,14 +145,14 @@ __global__ void __launch_bounds__(C::T, MIN_CTAS) fir_persist_kernel(const FirKe
         const unsigned int next_item = next_item_s;
         __syncthreads();
         inv_stage1<C>(v, t, a.tw1, tile);
-        store_slice<C, IO>(v, t, it.ya, it.yb, it.m0, a.g);
+        store_slice<C, IO, false>(v, t, it.ya, it.yb, it.m0, a.g, ex.shape);
         item = next_item;
     }
 }
 
 // 16 points per thread (fft_core16.cuh): 512 threads at <= 64 registers -> 32 warps per SM.
 template <class C, class MaskT, int MIN_CTAS, class IO = IoF32, bool SHAPED = false>
-__global__ void __launch_bounds__(C::T, MIN_CTAS) fir16_block_kernel(const FirKernelArgs a) {
+__global__ void __launch_bounds__(C::T, MIN_CTAS) fir16_block_kernel(const FirKernelArgs a, const FirExtra ex) {
     typedef typename IO::elem E;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cf* tile = reinterpret_cast<cf*>(smem_raw);
@@ -165,7 +171,7 @@ __global__ void __launch_bounds__(C::T, MIN_CTAS) fir16_block_kernel(const FirKe
     inv16_stage2<C>(v, t, a.tw2, tile);
     __syncthreads();
     inv16_stage1<C>(v, t, a.tw1, tile);
-    store_slice16<C, IO, SHAPED>(v, t, it.ya, it.yb, it.m0, a.g);
+    store_slice16<C, IO, SHAPED>(v, t, it.ya, it.yb, it.m0, a.g, ex.shape);
 }
 
 }  // namespace adt
