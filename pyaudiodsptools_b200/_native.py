@@ -13,7 +13,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libadt_b200.so")
+LIB_PATH = os.environ.get("ADT_LIB_PATH") or os.path.join(_HERE, "libadt_b200.so")   # override: A/B of builds
 NCCL_UNIQUE_ID_BYTES = 128
 
 

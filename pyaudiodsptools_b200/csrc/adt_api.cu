@@ -85,6 +85,7 @@ struct FirVariant {
     fir_kernel_fn cplx_i16, real_i16;  // 16-bit PCM in/out (IoI16)
     fir_kernel_fn persist_cplx, persist_real;  // persistent dynamic-queue variant (p32, float32 I/O) or null
     fir_kernel_fn shaped_cplx, shaped_real;    // float32 I/O with the wave-shaper store epilogue
+    fir_kernel_fn split_int_cplx, split_int_real, split_edge_cplx, split_edge_real;  // split launch (p32) or null
     void (*build)(const float* mask, bool real_only, HostTables& out);
 };
 
@@ -104,6 +105,10 @@ FirVariant make_variant32(const char* name) {
     v.persist_real = fir_persist_kernel<C, float, MIN_CTAS>;
     v.shaped_cplx = fir_block_kernel<C, cf, MIN_CTAS, IoF32, true>;
     v.shaped_real = fir_block_kernel<C, float, MIN_CTAS, IoF32, true>;
+    v.split_int_cplx = fir_split_kernel<C, cf, MIN_CTAS, true>;
+    v.split_int_real = fir_split_kernel<C, float, MIN_CTAS, true>;
+    v.split_edge_cplx = fir_split_kernel<C, cf, MIN_CTAS, false>;
+    v.split_edge_real = fir_split_kernel<C, float, MIN_CTAS, false>;
     v.build = [](const float* mask, bool real_only, HostTables& out) {
         out.tw1 = build_tw1<C>();
         out.tw2 = build_tw2<C>();
@@ -127,6 +132,7 @@ FirVariant make_variant16(const char* name) {
     v.persist_cplx = v.persist_real = nullptr;
     v.shaped_cplx = fir16_block_kernel<C, cf, MIN_CTAS, IoF32, true>;
     v.shaped_real = fir16_block_kernel<C, float, MIN_CTAS, IoF32, true>;
+    v.split_int_cplx = v.split_int_real = v.split_edge_cplx = v.split_edge_real = nullptr;
     v.build = [](const float* mask, bool real_only, HostTables& out) {
         out.tw1 = build16_tw1<C>();
         out.tw2 = build16_tw2<C>();
@@ -191,7 +197,8 @@ extern "C" int adt_ctx_create(int device, adt_ctx** out) {
     for (int vi = 0; vi < n_var; ++vi) {
         const FirVariant* v = &vars[vi];
         for (fir_kernel_fn f : {v->cplx, v->real, v->cplx_i16, v->real_i16, v->persist_cplx, v->persist_real,
-                                v->shaped_cplx, v->shaped_real}) {
+                                v->shaped_cplx, v->shaped_real, v->split_int_cplx, v->split_int_real,
+                                v->split_edge_cplx, v->split_edge_real}) {
             if (!f) continue;
             e = cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->smem);
             if (e == cudaSuccess && getenv("ADT_FIR_CARVEOUT"))  // tuning knob: % of the 228 KB given to shared memory
@@ -364,6 +371,8 @@ struct adt_fir {
 };
 
 __global__ void fir_set_counter(unsigned int* c, unsigned int v) { *c = v; }
+struct adt_fir;
+static fir_kernel_fn kp_used(adt_fir* f, fir_kernel_fn k);  // persistent kernel if `k` is it, else nullptr
 
 static int fir_launch(adt_fir* f, cudaStream_t s, const void* x, int64_t in_pitch, int64_t n_in, int64_t in_shift,
                       void* y, int64_t out_pitch, int64_t n_out, int32_t n_rows, bool i16 = false) {
@@ -425,10 +434,44 @@ static int fir_launch(adt_fir* f, cudaStream_t s, const void* x, int64_t in_pitc
         ex.work_counter = f->d_counter;
         k = kp;
     }
+    ex.blk_count = (int)blocks;
+    ex.blk_offset = ex.blk_skip_len = 0;
+    ex.blk_skip_from = (int)blocks;
+    // split launch: interior blocks by a kernel without any bounds code, edge blocks by the generic one
+    static const int split_mode = getenv("ADT_FIR_SPLIT") ? atoi(getenv("ADT_FIR_SPLIT")) : 0;
+    fir_kernel_fn k_int = f->d.mask_is_real ? f->var->split_int_real : f->var->split_int_cplx;
+    fir_kernel_fn k_edge = f->d.mask_is_real ? f->var->split_edge_real : f->var->split_edge_cplx;
+    if (split_mode && !i16 && !shaped && k_int && k != kp_used(f, k)) {
+        const int64_t N = f->d.fft_size, hop = f->d.hop, back = f->d.back;
+        int64_t b_lo = (back - in_shift + hop - 1) / hop;            // first block with ws >= 0
+        if (b_lo < 0) b_lo = 0;
+        int64_t b_hi = (n_in - N + back - in_shift) / hop + 1;        // one past the last block with ws + N <= n_in
+        if (n_in - N + back - in_shift < 0) b_hi = 0;
+        if (b_hi > n_out / hop) b_hi = n_out / hop;                   // ... and a full hop inside the output
+        if (b_hi > blocks) b_hi = blocks;
+        if (b_hi - b_lo >= 8 && (b_hi - b_lo) * pairs >= f->resident_ctas) {
+            FirExtra ei = ex, ee = ex;
+            ei.blk_count = (int)(b_hi - b_lo); ei.blk_offset = (int)b_lo; ei.blk_skip_from = ei.blk_count; ei.blk_skip_len = 0;
+            ee.blk_count = (int)(blocks - (b_hi - b_lo)); ee.blk_offset = 0; ee.blk_skip_from = (int)b_lo; ee.blk_skip_len = (int)(b_hi - b_lo);
+            k_int<<<(unsigned)(ei.blk_count * pairs), f->var->threads, f->var->smem, s>>>(a, ei);
+            CK(ctx, cudaGetLastError());
+            ctx->launches++;
+            if (ee.blk_count > 0) {
+                k_edge<<<(unsigned)(ee.blk_count * pairs), f->var->threads, f->var->smem, s>>>(a, ee);
+                CK(ctx, cudaGetLastError());
+                ctx->launches++;
+            }
+            return ADT_OK;
+        }
+    }
     k<<<grid, f->var->threads, f->var->smem, s>>>(a, ex);
     CK(ctx, cudaGetLastError());
     ctx->launches++;
     return ADT_OK;
+}
+
+static fir_kernel_fn kp_used(adt_fir* f, fir_kernel_fn k) {
+    return (k == f->var->persist_real || k == f->var->persist_cplx) ? k : nullptr;
 }
 
 extern "C" int adt_fir_destroy(adt_fir* f) {

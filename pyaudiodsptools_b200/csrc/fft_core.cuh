@@ -400,6 +400,19 @@ ADT_HD void load_window(cf* v, int t, const typename IO::elem* __restrict__ xa,
     }
 }
 
+// interior blocks only: the whole window is inside [0, n_in) — no bounds code in the kernel at all
+template <class C, class IO = IoF32>
+ADT_HD void load_window_interior(cf* v, int t, const typename IO::elem* __restrict__ xa,
+                                 const typename IO::elem* __restrict__ xb, long long ws) {
+    static_for<0, C::B1>([&](auto U) {
+        static_for<0, C::N1>([&](auto K) {
+            constexpr int u = decltype(U)::value, n1 = decltype(K)::value;
+            const long long s = ws + n1 * C::M1 + t + u * C::T;
+            v[u * C::N1 + n1] = mk(IO::load(xa + s), xb ? IO::load(xb + s) : 0.0f);
+        });
+    });
+}
+
 // ---- phase 1: forward stage 1, write tile ----------------------------------
 template <class C>
 ADT_HD void fwd_stage1(cf* v, int t, const cf* __restrict__ tw1, cf* tile) {

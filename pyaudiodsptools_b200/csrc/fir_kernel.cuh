@@ -40,6 +40,9 @@ struct FirKernelArgs {
 struct FirExtra {
     unsigned int* work_counter;  // persistent variant: next unclaimed item (preset to gridDim.x by the host)
     FirShape shape;              // SHAPED kernels: wave-shaper applied to every output sample before the store
+    // split launch (fir_split_kernel): this launch covers `blk_count` time blocks per row, namely
+    // blk = e + blk_offset for e < blk_skip_from, and e + blk_offset + blk_skip_len after that
+    int blk_count, blk_offset, blk_skip_from, blk_skip_len;
 };
 
 // Work item -> (time block, channel pair).  Time block is the fast index so CTAs that run
@@ -148,6 +151,64 @@ __global__ void __launch_bounds__(C::T, MIN_CTAS) fir_persist_kernel(const FirKe
         store_slice<C, IO, false>(v, t, it.ya, it.yb, it.m0, a.g, ex.shape);
         item = next_item;
     }
+}
+
+// SPLIT launch (opt-in, ADT_FIR_SPLIT=1): an interior-only kernel (INTERIOR = true) handles every block whose
+// window lies inside the input and whose hop lies inside the output — it contains no bounds code — and the
+// same kernel with INTERIOR = false handles the one or two edge blocks per row.
+template <class E>
+__device__ __forceinline__ FirItem<E> fir_item_split(const FirKernelArgs& a, const FirExtra& ex, long long item) {
+    FirItem<E> it;
+    int blk = (int)(item % ex.blk_count);
+    const int row_a = 2 * (int)(item / ex.blk_count), row_b = row_a + 1;
+    blk += ex.blk_offset + (blk >= ex.blk_skip_from ? ex.blk_skip_len : 0);
+    const bool has_b = row_b < a.n_rows;
+    const E* x = static_cast<const E*>(a.x);
+    E* y = static_cast<E*>(a.y);
+    it.xa = x + (long long)row_a * a.g.in_pitch;
+    it.xb = has_b ? x + (long long)row_b * a.g.in_pitch : nullptr;
+    it.ya = y + (long long)row_a * a.g.out_pitch;
+    it.yb = has_b ? y + (long long)row_b * a.g.out_pitch : nullptr;
+    it.m0 = (long long)blk * a.g.hop;
+    it.ws = it.m0 - a.g.back + a.g.in_shift;
+    return it;
+}
+
+template <class C, class MaskT, int MIN_CTAS, bool INTERIOR>
+__global__ void __launch_bounds__(C::T, MIN_CTAS) fir_split_kernel(const FirKernelArgs a, const FirExtra ex) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cf* tile = reinterpret_cast<cf*>(smem_raw);
+    const int t = threadIdx.x;
+    const long long item = blockIdx.x;
+    const FirItem<float> it = fir_item_split<float>(a, ex, item);
+    cf v[32];
+    if constexpr (INTERIOR)
+        load_window_interior<C, IoF32>(v, t, it.xa, it.xb, it.ws);
+    else
+        load_window<C, IoF32>(v, t, it.xa, it.xb, it.ws, a.g.n_in);
+    if (a.prefetch_ahead > 0 && t < 2) {   // same bulk L2 prefetch, in this launch's own item numbering
+        const long long nxt = item + a.prefetch_ahead;
+        if (nxt < (long long)ex.blk_count * ((a.n_rows + 1) / 2)) {
+            const FirItem<float> nx = fir_item_split<float>(a, ex, nxt);
+            const float* base = t ? nx.xb : nx.xa;
+            long long lo = nx.ws < 0 ? 0 : nx.ws, hi = nx.ws + C::N;
+            if (hi > a.g.n_in) hi = a.g.n_in;
+            lo = (lo + 3) & ~3LL;
+            const long long cnt = (hi - lo) & ~3LL;
+            if (base && cnt > 0)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + lo), "r"((unsigned)(cnt * 4)) : "memory");
+        }
+    }
+    fwd_stage1<C>(v, t, a.tw1, tile);
+    __syncthreads();
+    fwd_stage2<C>(v, t, a.tw2, tile);
+    __syncwarp();
+    mid_stage3<C, MaskT>(v, t, reinterpret_cast<const MaskT*>(a.mask), tile);
+    __syncwarp();
+    inv_stage2<C>(v, t, a.tw2, tile);
+    __syncthreads();
+    inv_stage1<C>(v, t, a.tw1, tile);
+    store_slice<C, IoF32, false>(v, t, it.ya, it.yb, it.m0, a.g, ex.shape);
 }
 
 // 16 points per thread (fft_core16.cuh): 512 threads at <= 64 registers -> 32 warps per SM.
