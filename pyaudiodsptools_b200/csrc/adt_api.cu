@@ -357,7 +357,7 @@ struct adt_fir {
     cf* d_tw2 = nullptr;
     // streaming state: two [n_channels][hist_pitch] buffers (history ++ newest chunk)
     FirShape shape{0, 0, 0.f, 0.f, 0.f, 0.f};  // store epilogue (adt_fir_set_epilogue)
-    unsigned int* d_counter = nullptr;  // work queue head of the persistent variant
+    unsigned int* d_counter = nullptr;  // work queue heads of the persistent variant, one per stream slot
     int resident_ctas = 0;  // CTAs resident at once (SMs x CTAs per SM), computed on first launch
     float* d_hist[2] = {nullptr, nullptr};
     int cur = 0;
@@ -371,11 +371,12 @@ struct adt_fir {
 };
 
 __global__ void fir_set_counter(unsigned int* c, unsigned int v) { *c = v; }
-struct adt_fir;
-static fir_kernel_fn kp_used(adt_fir* f, fir_kernel_fn k);  // persistent kernel if `k` is it, else nullptr
 
+
+// slot: 0 = the context stream, 1 + i = copy stream i (launches on different streams may overlap, so
+// per-launch device state — the persistent variant's work counter — exists once per slot)
 static int fir_launch(adt_fir* f, cudaStream_t s, const void* x, int64_t in_pitch, int64_t n_in, int64_t in_shift,
-                      void* y, int64_t out_pitch, int64_t n_out, int32_t n_rows, bool i16 = false) {
+                      void* y, int64_t out_pitch, int64_t n_out, int32_t n_rows, bool i16 = false, int slot = 0) {
     adt_ctx* ctx = f->ctx;
     if (n_rows <= 0 || n_out <= 0) return ADT_OK;
     const int64_t blocks = (n_out + f->d.hop - 1) / f->d.hop;
@@ -425,14 +426,15 @@ static int fir_launch(adt_fir* f, cudaStream_t s, const void* x, int64_t in_pitc
     // measured: +1.5 % for the 1-CTA/SM N = 16384 kernel, -5 % for N = 8192 -> default on for 16384 only
     const int persist_mode = getenv("ADT_FIR_PERSIST") ? atoi(getenv("ADT_FIR_PERSIST")) : (f->d.fft_size == 16384);
     fir_kernel_fn kp = f->d.mask_is_real ? f->var->persist_real : f->var->persist_cplx;
+    bool persistent = false;
     if (persist_mode && !i16 && !shaped && kp && a.n_items >= 4LL * f->resident_ctas) {
-        if (!f->d_counter) CK(ctx, cudaMalloc((void**)&f->d_counter, sizeof(unsigned int)));
+        if (!f->d_counter) CK(ctx, cudaMalloc((void**)&f->d_counter, (ADT_COPY_STREAMS + 1) * sizeof(unsigned int)));
         grid = (unsigned)f->resident_ctas;
-        const unsigned int init = grid;
-        fir_set_counter<<<1, 1, 0, s>>>(f->d_counter, init);
+        fir_set_counter<<<1, 1, 0, s>>>(f->d_counter + slot, grid);   // first unclaimed item = grid size
         ctx->launches++;
-        ex.work_counter = f->d_counter;
+        ex.work_counter = f->d_counter + slot;
         k = kp;
+        persistent = true;
     }
     ex.blk_count = (int)blocks;
     ex.blk_offset = ex.blk_skip_len = 0;
@@ -441,7 +443,7 @@ static int fir_launch(adt_fir* f, cudaStream_t s, const void* x, int64_t in_pitc
     static const int split_mode = getenv("ADT_FIR_SPLIT") ? atoi(getenv("ADT_FIR_SPLIT")) : 0;
     fir_kernel_fn k_int = f->d.mask_is_real ? f->var->split_int_real : f->var->split_int_cplx;
     fir_kernel_fn k_edge = f->d.mask_is_real ? f->var->split_edge_real : f->var->split_edge_cplx;
-    if (split_mode && !i16 && !shaped && k_int && k != kp_used(f, k)) {
+    if (split_mode && !i16 && !shaped && !persistent && k_int) {
         const int64_t N = f->d.fft_size, hop = f->d.hop, back = f->d.back;
         int64_t b_lo = (back - in_shift + hop - 1) / hop;            // first block with ws >= 0
         if (b_lo < 0) b_lo = 0;
@@ -468,10 +470,6 @@ static int fir_launch(adt_fir* f, cudaStream_t s, const void* x, int64_t in_pitc
     CK(ctx, cudaGetLastError());
     ctx->launches++;
     return ADT_OK;
-}
-
-static fir_kernel_fn kp_used(adt_fir* f, fir_kernel_fn k) {
-    return (k == f->var->persist_real || k == f->var->persist_cplx) ? k : nullptr;
 }
 
 extern "C" int adt_fir_destroy(adt_fir* f) {
@@ -642,7 +640,7 @@ static int fir_process_host_impl(adt_fir* f, const void* xv, int64_t in_pitch, i
         if (n_in > 0)
             CK(ctx, cudaMemcpy2DAsync(f->d_in[si], din_pitch * es, x + (size_t)r0 * in_pitch * es, in_pitch * es,
                                       n_in * es, rows, cudaMemcpyHostToDevice, s));
-        rc = fir_launch(f, s, f->d_in[si], din_pitch, n_in, 0, f->d_out[si], dout_pitch, n_out, rows, i16);
+        rc = fir_launch(f, s, f->d_in[si], din_pitch, n_in, 0, f->d_out[si], dout_pitch, n_out, rows, i16, 1 + si);
         if (rc) return rc;
         CK(ctx, cudaMemcpy2DAsync(y + (size_t)r0 * out_pitch * es, out_pitch * es, f->d_out[si], dout_pitch * es,
                                   n_out * es, rows, cudaMemcpyDeviceToHost, s));

@@ -181,6 +181,40 @@ def test_linearity_and_shift_invariance_large(gpu_lib):
         assert rms(ya[ch] - want) <= RMS_TOL
 
 
+_PERSIST_WORKER = r"""
+import sys
+sys.path.insert(0, {root!r})
+import numpy as np
+import pyaudiodsptools_b200 as adt
+import oracle
+from scipy.signal import fftconvolve
+fs, c, rows, n = 44100, 4096, 240, 441000
+adt.config.initialize(fs, c)
+dev = adt.CreateLowCutFilter(800, channels=rows)
+x = np.random.default_rng(1).uniform(-1, 1, (rows, n)).astype(np.float32)
+y = dev.process(x)                      # 3+ row groups on concurrent copy streams, each a persistent launch
+taps, d = oracle.lowcut_taps(fs, c, 800), oracle.stream_delay(c)
+for ch in (0, 75, 76, 151, 152, rows - 1):
+    want = np.zeros(y.shape[1]); full = fftconvolve(x[ch].astype(np.float64), taps); want[d:] = full[: y.shape[1] - d]
+    err = float(np.sqrt(np.mean((y[ch] - want) ** 2)))
+    assert err <= 2e-6, (ch, err)
+print("persistent host pipeline ok")
+"""
+
+
+def test_persistent_variant_on_concurrent_streams(gpu_lib, tmp_path):
+    """The dynamic-queue persistent kernel keeps one work counter per stream slot: row groups of
+    process() run on three copy streams at once (regression test for a shared-counter race)."""
+    import os, subprocess, sys
+    from conftest import ROOT
+    script = tmp_path / "p.py"
+    script.write_text(_PERSIST_WORKER.format(root=ROOT))
+    env = dict(os.environ, ADT_FIR_PERSIST="1", ADT_FIR_GROUP_MB="128")
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "persistent host pipeline ok" in r.stdout
+
+
 def test_device_resident_whole_buffer(gpu_lib):
     fs, c, rows, n = 44100, 4096, 9, 5 * 4096
     adt.config.initialize(fs, c)
