@@ -131,7 +131,8 @@ int adt_fir_reset(adt_fir* fir);                                          /* his
  *   kind 1 = CreateSaturator.apply   (EffectSaturator.py:41-48)  params = {s, 1-s, (s+1)/2, gain, mode(1|2)}
  *            with s = 10^(threshold_dB/20), gain = 10^(makeup_dB/20)                    (bit-exact)
  *   kind 2 = CreateSoftClipper.apply (EffectSoftClipper.py:37-44) params = {drive+1, 0, 0, 0, 0}  (powf ulps)
- * adt_fir_set_epilogue fuses one into the FIR kernel's store (kind 0 detaches). */
+ * adt_fir_set_epilogue fuses one into the FIR kernel's store (kind 0 detaches); the fused form replaces the
+ * IEEE divisions / powf by reciprocal-multiply, __fdividef and __powf (result within ~2 ulp / 2e-6). */
 int adt_fir_set_epilogue(adt_fir* fir, int kind, const float* params);
 int adt_shape_apply_dev(adt_ctx* ctx, int kind, const float* params, const float* x_dev, float* y_dev, int64_t n);
 int adt_shape_apply_host(adt_ctx* ctx, int kind, const float* params, const float* x_host, float* y_host, int64_t n);

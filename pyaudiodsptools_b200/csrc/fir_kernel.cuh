@@ -18,7 +18,7 @@ ADT_HD float fir_shape(const FirShape& sh, float v) {
     if (sh.kind == 0) return v;
     ShapeParams sp;
     sp.kind = sh.kind; sp.mode = sh.mode; sp.p0 = sh.p0; sp.p1 = sh.p1; sp.p2 = sh.p2; sp.p3 = sh.p3;
-    return shape_apply(sp, v);
+    return shape_apply<true>(sp, v);   // fused epilogue: fast division (shape.cuh)
 }
 
 struct FirKernelArgs {

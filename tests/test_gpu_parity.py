@@ -315,7 +315,8 @@ def test_fused_epilogue_equals_separate_pass(gpu_lib):
         plain = adt.CreateHighCutFilter(6000, channels=5)
         fused = adt.CreateHighCutFilter(6000, channels=5, epilogue=shaper)
         y = plain.process(x)
-        assert np.array_equal(fused.process(x), shaper.apply(y))           # identical: same kernel, same formula
+        # fused = same filter kernel + the shaper with fast division / __powf in the store phase
+        assert np.max(np.abs(fused.process(x) - shaper.apply(y))) <= 3e-6
         ys = np.concatenate([fused.apply(np.pad(x, ((0, 0), (0, 5 * c - x.shape[1])))[:, i:i + c])
                              for i in range(0, 5 * c, c)], axis=1)
         assert rms(ys - shaper.apply(y)) <= 1e-6
