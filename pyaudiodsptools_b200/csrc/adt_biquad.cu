@@ -3,8 +3,9 @@
 // adt_biquad object, batched over channels.
 //
 // The recurrence is sequential in time, so the unit of parallelism is the
-// channel: one thread per channel.  To keep HBM accesses coalesced a warp owns
-// 32 channels and walks time in tiles of 32 samples: the tile is loaded
+// channel: one thread per channel.  To keep HBM accesses coalesced a warp (one
+// CTA) owns 32 channels and walks time in tiles of 32 samples, with the next
+// tile's loads in flight while the current one is filtered: the tile is loaded
 // row-wise (32 consecutive samples of one channel = one 128-byte line per warp
 // instruction), transposed through shared memory (pitch 33, conflict free),
 // filtered column-wise in registers, and stored back row-wise.
@@ -34,28 +35,39 @@ template <>
 __device__ __forceinline__ double round_to<double>(double v) { return v; }
 
 // state: [n_channels][5] doubles = x[n-1], x[n-2], x[n-3], y[n-1], y[n-2]
+// One warp per CTA (32 channels); the global loads of tile k+1 are issued into registers before tile k is
+// filtered, so HBM latency hides behind the fp64 recurrence (the real bound: ~40 dependent cycles/sample).
 template <typename T>
-__global__ void __launch_bounds__(128) biquad_kernel(const T* __restrict__ x, T* __restrict__ y, long long pitch,
-                                                     long long n, int n_channels, BiquadCoef k,
-                                                     double* __restrict__ state) {
-    __shared__ T tile[4][32][33];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c0 = (blockIdx.x * 4 + warp) * 32;
+__global__ void __launch_bounds__(32) biquad_kernel(const T* __restrict__ x, T* __restrict__ y, long long pitch,
+                                                    long long n, int n_channels, BiquadCoef k,
+                                                    double* __restrict__ state) {
+    __shared__ T tl[32][33];
+    const int lane = threadIdx.x;
+    const int c0 = blockIdx.x * 32;
     if (c0 >= n_channels) return;
     const int ch = c0 + lane;
     const bool live = ch < n_channels;
-    T(*tl)[33] = tile[warp];
     double x1 = 0, x2 = 0, x3 = 0, y1 = 0, y2 = 0;
     if (live) {
         const double* s = state + (long long)ch * 5;
         x1 = s[0]; x2 = s[1]; x3 = s[2]; y1 = s[3]; y2 = s[4];
     }
     const int rows = min(32, n_channels - c0);
+    const T* xr = x + (long long)c0 * pitch + lane;
+    T* yr = y + (long long)c0 * pitch + lane;
+    T nxt[32];
+    // prologue: tile 0 into registers (row i of the tile = 32 consecutive samples of channel c0 + i)
+#pragma unroll
+    for (int i = 0; i < 32; ++i) nxt[i] = (i < rows && lane < n) ? xr[(long long)i * pitch] : T(0);
     for (long long base = 0; base < n; base += 32) {
         const int w = (int)min((long long)32, n - base);
-        for (int i = 0; i < rows; ++i)
-            if (lane < w) tl[i][lane] = x[(long long)(c0 + i) * pitch + base + lane];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) tl[i][lane] = nxt[i];
         __syncwarp();
+        // prefetch the next tile while this one is filtered
+        const long long nb = base + 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) nxt[i] = (i < rows && nb + lane < n) ? xr[(long long)i * pitch + nb] : T(0);
         if (live) {
             for (int j = 0; j < w; ++j) {
                 const double xin = (double)tl[lane][j];
@@ -72,8 +84,9 @@ __global__ void __launch_bounds__(128) biquad_kernel(const T* __restrict__ x, T*
             }
         }
         __syncwarp();
-        for (int i = 0; i < rows; ++i)
-            if (lane < w) y[(long long)(c0 + i) * pitch + base + lane] = tl[i][lane];
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (i < rows && lane < w) yr[(long long)i * pitch + base] = tl[i][lane];
         __syncwarp();
     }
     if (live) {
@@ -140,12 +153,12 @@ extern "C" int adt_biquad_apply_dev(adt_biquad* b, const void* x, void* y, int64
     adt_ctx* ctx = b->ctx;
     if (n == 0) return ADT_OK;
     ADT_CK(ctx, cudaSetDevice(ctx->device));
-    const unsigned grid = (unsigned)((b->n_channels + 127) / 128);
+    const unsigned grid = (unsigned)((b->n_channels + 31) / 32);
     if (b->f64)
-        biquad_kernel<double><<<grid, 128, 0, ctx->stream>>>((const double*)x, (double*)y, pitch, n, b->n_channels, b->k,
+        biquad_kernel<double><<<grid, 32, 0, ctx->stream>>>((const double*)x, (double*)y, pitch, n, b->n_channels, b->k,
                                                              b->d_state);
     else
-        biquad_kernel<float><<<grid, 128, 0, ctx->stream>>>((const float*)x, (float*)y, pitch, n, b->n_channels, b->k,
+        biquad_kernel<float><<<grid, 32, 0, ctx->stream>>>((const float*)x, (float*)y, pitch, n, b->n_channels, b->k,
                                                             b->d_state);
     ADT_CK(ctx, cudaGetLastError());
     ctx->launches++;
