@@ -17,6 +17,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
 
 
+def pytest_sessionstart(session):
+    """The C-ABI library is git-ignored (built in-tree, it travels to the GPU box with the snapshot): on a
+    fresh checkout build it once (nvcc cross-compiles for sm_100a without a GPU, ~90 s)."""
+    lib = os.path.join(ROOT, "pyaudiodsptools_b200", "libadt_b200.so")
+    if not os.path.exists(lib) and not os.environ.get("ADT_LIB_PATH"):
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "pyaudiodsptools_b200", "csrc"), "-j4"])
+
+
 def load_golden(name):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     meta = json.loads(str(z["meta"]))
