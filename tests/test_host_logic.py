@@ -130,3 +130,45 @@ def test_product_never_imports_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(import|from)\s+oracle\b", src, re.M), fn
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/adt_b200.h is the drop-in boundary: it must compile as C (no C++ / CUDA / torch types) and
+    a C program must link against the shared library; device count works without a GPU."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include "adt_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) { int n = -1; adt_fir_desc d = {8192, 6144, 1024, 5120, 1, 4096, 1, 0};\n'
+                   '  if (adt_device_count(&n) != ADT_OK || d.hop != 6144) return 1;\n'
+                   '  printf("%s devices=%d %s\\n", adt_version(), n, adt_status_string(ADT_ERR_UNSUPPORTED)); return 0; }\n')
+    exe = tmp_path / "abi"
+    lib_dir = os.path.dirname(_native.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe), "-L", lib_dir, "-l:libadt_b200.so", f"-Wl,-rpath,{lib_dir}"])
+    out = subprocess.check_output([str(exe)], text=True)
+    assert out.startswith("adt_b200") and "unsupported geometry" in out
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_block_plan_random_filters(seed):
+    """plan_block for arbitrary (also non-symmetric, even-length) FIRs and delays: overlap-save replay of the
+    plan equals the direct convolution."""
+    rng = np.random.default_rng(seed)
+    t = int(rng.integers(1, 6000))
+    taps = rng.standard_normal(t)
+    if seed % 3 == 0 and t % 2 == 1:
+        taps = taps + taps[::-1]                       # symmetric -> real mask
+    delay = int(rng.integers(0, 5000))
+    fft = [4096, 8192, 16384][seed % 3]
+    if t + 64 > fft:
+        fft = 16384
+    plan = design.plan_block(taps, delay, fft)
+    assert plan.n0 + plan.hop <= plan.fft_size and plan.hop % 32 == 0 and plan.n0 % 32 == 0
+    n = 3 * plan.hop + 1234
+    x = rng.uniform(-1, 1, n)
+    want = np.zeros(n)
+    full = np.convolve(x, taps)
+    want[delay:] = full[: n - delay]
+    got = _overlap_save_numpy(plan, x, n)
+    scale = np.sqrt(np.mean(want ** 2)) + 1e-30
+    assert rms(got - want) / scale < 2e-6       # complex64 mask rounding only
