@@ -112,6 +112,29 @@ def test_other_chunk_sizes(gpu_lib, chunk, kind):
     assert rms(ys - y) <= 1e-6
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_engine_with_arbitrary_filters(gpu_lib, seed):
+    """The FIR engine is generic (y[m] = sum_k h[k] x[m - D - k]): random non-symmetric / even-length taps,
+    every kernel size, against numpy.convolve."""
+    from pyaudiodsptools_b200 import design, devices
+    rng = np.random.default_rng(seed)
+    chunk = [512, 1024, 4096][seed % 3]
+    t = int(rng.integers(2, chunk - 4))
+    taps = rng.standard_normal(t) / np.sqrt(t)
+    fft = [4096, 8192, 16384][(seed // 2) % 3]
+    dev = devices._FirDevice(taps, chunk, channels=3, fft_size=fft)
+    assert dev.plan.mask_is_real == bool(t % 2 == 1 and np.allclose(taps, taps[::-1]))
+    n = 5 * chunk + 17
+    x = rng.uniform(-1, 1, (3, n)).astype(np.float32)
+    y = dev.process(x)
+    d = design.stream_delay(chunk)
+    for ch in range(3):
+        want = np.zeros(y.shape[1])
+        full = np.convolve(x[ch].astype(np.float64), taps)
+        want[d:] = full[: y.shape[1] - d]
+        assert rms(y[ch] - want) <= 3e-6 * max(1.0, rms(want))
+
+
 def test_eq_batched_stereo_pairs(gpu_lib):
     # BASELINE config 5 shape in miniature: 96 kHz, stereo = two planar rows per stream
     fs, c = 96000, 4096
