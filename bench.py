@@ -95,17 +95,20 @@ def run_reference_arm(args, wl, rank):
     import multiprocessing as mp
     cores = len(os.sched_getaffinity(0))
     kind, ctor_args, fs, chunk, channels, seconds, desc = wl
-    per_core = 25                       # ~1 s of CPU work per core per step
+    budget_s = 120.0                    # whole timed region, whatever K is
     with mp.get_context("fork").Pool(cores) as pool:
-        for _ in range(args.warmup):
-            cpu_throughput(wl, 1, pool, cores)
+        t1 = None
+        for _ in range(max(1, args.warmup)):          # warm-up steps of one channel per core, last one timed
+            _, t1 = cpu_throughput(wl, 1, pool, cores)
+        per_core = int(max(1, min(25, budget_s / max(args.steps, 1) / max(t1, 1e-3))))
         tot, tt = 0, 0.0
         for _ in range(args.steps):
             d, dt = cpu_throughput(wl, per_core, pool, cores)
             tot += d
             tt += dt
     v = tot / tt / 1e6
-    sample = f"{per_core * cores} channels x {fs * seconds} samples per step over {cores} processes (one device object per channel)"
+    sample = (f"{per_core * cores} channels x {fs * seconds} samples per step over {cores} processes (one device object "
+              f"per channel; channels per step sized so that {args.steps} steps take about {budget_s:.0f} s)")
     line = {
         "impl": "reference", "metric": "Msamples/s overlap-add FFT filter, chunk=%d" % chunk, "value": v,
         "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
