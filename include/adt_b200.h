@@ -59,6 +59,9 @@ int adt_ctx_sync(adt_ctx* ctx);
 /* number of this library's kernels launched on ctx since creation */
 int adt_ctx_launch_count(adt_ctx* ctx, uint64_t* count);
 int adt_ctx_device_name(adt_ctx* ctx, char* buf, size_t len);
+/* "domain:bus:device.function" of the context's GPU (len >= 13): lets the host side find the GPU's NUMA
+ * node under /sys/bus/pci/devices/ and keep pinned staging buffers and the calling thread next to it */
+int adt_ctx_pci_bus_id(adt_ctx* ctx, char* buf, size_t len);
 
 /* ---- memory (no torch / cupy to lean on) --------------------------------- */
 int adt_malloc(adt_ctx* ctx, size_t bytes, void** dptr);
@@ -174,6 +177,13 @@ int adt_comm_scatter_rows(adt_comm* comm, const float* full_dev_on_root, float* 
                           int64_t pitch, int32_t root);
 int adt_comm_gather_rows(adt_comm* comm, const float* shard_dev, float* full_dev_on_root, int64_t rows_per_rank,
                          int64_t pitch, int32_t root);
+/* uneven shards (what sharding.channel_range produces when channels % (2*world) != 0): rank r owns
+ * row_counts[r] rows, stored back to back in the root's matrix; row_counts has `world` entries and must be
+ * identical on every rank.  Ranks with zero rows take no part in the exchange. */
+int adt_comm_scatterv_rows(adt_comm* comm, const float* full_dev_on_root, float* shard_dev, const int64_t* row_counts,
+                           int64_t pitch, int32_t root);
+int adt_comm_gatherv_rows(adt_comm* comm, const float* shard_dev, float* full_dev_on_root, const int64_t* row_counts,
+                          int64_t pitch, int32_t root);
 int adt_comm_broadcast(adt_comm* comm, void* buf_dev, size_t bytes, int32_t root);
 int adt_comm_barrier(adt_comm* comm);
 

@@ -42,6 +42,7 @@ PROTOTYPES = {
     "adt_ctx_sync": (C.c_int, [_P]),
     "adt_ctx_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "adt_ctx_device_name": (C.c_int, [_P, C.c_char_p, C.c_size_t]),
+    "adt_ctx_pci_bus_id": (C.c_int, [_P, C.c_char_p, C.c_size_t]),
     "adt_malloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
     "adt_free": (C.c_int, [_P, _P]),
     "adt_malloc_host": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
@@ -80,6 +81,8 @@ PROTOTYPES = {
     "adt_comm_destroy": (C.c_int, [_P]),
     "adt_comm_scatter_rows": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int32]),
     "adt_comm_gather_rows": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int32]),
+    "adt_comm_scatterv_rows": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int64), C.c_int64, C.c_int32]),
+    "adt_comm_gatherv_rows": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int64), C.c_int64, C.c_int32]),
     "adt_comm_broadcast": (C.c_int, [_P, _P, C.c_size_t, C.c_int32]),
     "adt_comm_barrier": (C.c_int, [_P]),
 }
@@ -169,6 +172,10 @@ class Context:
         assert host.flags["C_CONTIGUOUS"]
         self.check(self.lib.adt_memcpy_d2h(self.h, host.ctypes.data, dptr, host.nbytes))
 
+    def d2d(self, dst: int, src: int, nbytes: int):
+        """Asynchronous device-to-device copy on the context stream."""
+        self.check(self.lib.adt_memcpy_d2d(self.h, dst, src, nbytes))
+
     def sync(self):
         self.check(self.lib.adt_ctx_sync(self.h))
 
@@ -182,9 +189,57 @@ class Context:
         self.check(self.lib.adt_ctx_device_name(self.h, buf, 256))
         return buf.value.decode()
 
+    def pci_bus_id(self) -> str:
+        buf = C.create_string_buffer(32)
+        self.check(self.lib.adt_ctx_pci_bus_id(self.h, buf, 32))
+        return buf.value.decode().lower()
+
+    def bind_host_to_gpu_numa(self):
+        """Pin the calling process to the CPUs of the GPU's NUMA node, so that page-locked staging buffers
+        allocated afterwards (first touch / local allocation policy) and the thread that feeds the copy
+        engines sit next to the GPU's PCIe root.  Returns a dict describing what was done (for bench.py);
+        never raises: on boxes without NUMA information it is a no-op."""
+        info = {"pci": None, "numa_node": None, "cpus": None, "bound": False}
+        try:
+            bus = self.pci_bus_id()
+            info["pci"] = bus
+            with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+                node = int(f.read().strip())
+            info["numa_node"] = node
+            if node < 0:
+                return info
+            with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+                cpus = _parse_cpulist(f.read().strip())
+            allowed = os.sched_getaffinity(0) & cpus
+            info["cpus"] = len(allowed)
+            if allowed:
+                os.sched_setaffinity(0, allowed)
+                info["bound"] = True
+                try:   # prefer the node for every later allocation of this process (MPOL_PREFERRED = 1)
+                    libc = C.CDLL(None, use_errno=True)
+                    mask = C.c_ulong(1 << node)
+                    rc = libc.syscall(238, 1, C.byref(mask), C.c_ulong(8 * C.sizeof(C.c_ulong)))
+                    info["mempolicy"] = "preferred" if rc == 0 else f"errno {C.get_errno()}"
+                except Exception as e:  # pragma: no cover
+                    info["mempolicy"] = f"unavailable: {e}"
+        except Exception as e:
+            info["error"] = str(e)
+        return info
+
     # -- events ------------------------------------------------------------
     def event(self):
         return Event(self)
+
+
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.split(","):
+        part = part.strip()
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
 
 
 def _free_pinned(lib, ctx_h, p):

@@ -14,8 +14,7 @@
 #include "../../include/adt_b200.h"
 #include "adt_internal.h"
 #define CK ADT_CK
-#include "fir_kernel.cuh"
-#include "fir_tables.h"
+#include "fir_variants.cuh"
 
 using namespace adt;
 
@@ -38,7 +37,9 @@ int adt_cuda_fail(adt_ctx* ctx, cudaError_t e, const char* what) {
     return adt_set_error(ctx, ADT_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
 }
 
-extern "C" const char* adt_version(void) { return "adt_b200 0.1 (sm_100a)"; }
+extern "C" const char* adt_version(void) {
+    return ADT_AB_VARIANTS ? "adt_b200 0.2 (sm_100a, ab_variants=1)" : "adt_b200 0.2 (sm_100a, ab_variants=0)";
+}
 
 extern "C" const char* adt_status_string(int s) {
     switch (s) {
@@ -70,84 +71,13 @@ extern "C" int adt_device_count(int* count) {
 // ---------------------------------------------------------------------------
 namespace {
 
-typedef void (*fir_kernel_fn)(const FirKernelArgs, const FirExtra);
-
-struct HostTables {
-    std::vector<cf> tw1, tw2;
-    std::vector<float> coef_s, coef_x;  // kernel-order mask (and, 16-point variant, the cross coefficients)
-};
-
-struct FirVariant {
-    const char* name;
-    int n, threads;
-    size_t smem;
-    fir_kernel_fn cplx, real;
-    fir_kernel_fn cplx_i16, real_i16;  // 16-bit PCM in/out (IoI16)
-    fir_kernel_fn persist_cplx, persist_real;  // persistent dynamic-queue variant (p32, float32 I/O) or null
-    fir_kernel_fn shaped_cplx, shaped_real;    // float32 I/O with the wave-shaper store epilogue
-    fir_kernel_fn split_int_cplx, split_int_real, split_edge_cplx, split_edge_real;  // split launch (p32) or null
-    void (*build)(const float* mask, bool real_only, HostTables& out);
-};
-
-// 32 points per thread (fft_core.cuh)
-template <class C, int MIN_CTAS>
-FirVariant make_variant32(const char* name) {
-    FirVariant v;
-    v.name = name;
-    v.n = C::N;
-    v.threads = C::T;
-    v.smem = (size_t)C::TILE * sizeof(cf);
-    v.cplx = fir_block_kernel<C, cf, MIN_CTAS>;
-    v.real = fir_block_kernel<C, float, MIN_CTAS>;
-    v.cplx_i16 = fir_block_kernel<C, cf, MIN_CTAS, IoI16>;
-    v.real_i16 = fir_block_kernel<C, float, MIN_CTAS, IoI16>;
-    v.persist_cplx = fir_persist_kernel<C, cf, MIN_CTAS>;
-    v.persist_real = fir_persist_kernel<C, float, MIN_CTAS>;
-    v.shaped_cplx = fir_block_kernel<C, cf, MIN_CTAS, IoF32, true>;
-    v.shaped_real = fir_block_kernel<C, float, MIN_CTAS, IoF32, true>;
-    v.split_int_cplx = fir_split_kernel<C, cf, MIN_CTAS, true>;
-    v.split_int_real = fir_split_kernel<C, float, MIN_CTAS, true>;
-    v.split_edge_cplx = fir_split_kernel<C, cf, MIN_CTAS, false>;
-    v.split_edge_real = fir_split_kernel<C, float, MIN_CTAS, false>;
-    v.build = [](const float* mask, bool real_only, HostTables& out) {
-        out.tw1 = build_tw1<C>();
-        out.tw2 = build_tw2<C>();
-        out.coef_s = permute_mask<C>(mask, real_only);
-        out.coef_x.clear();
-    };
-    return v;
-}
-// 16 points per thread (fft_core16.cuh)
-template <class C, int MIN_CTAS>
-FirVariant make_variant16(const char* name) {
-    FirVariant v;
-    v.name = name;
-    v.n = C::N;
-    v.threads = C::T;
-    v.smem = (size_t)C::TILE * sizeof(cf);
-    v.cplx = fir16_block_kernel<C, cf, MIN_CTAS>;
-    v.real = fir16_block_kernel<C, float, MIN_CTAS>;
-    v.cplx_i16 = fir16_block_kernel<C, cf, MIN_CTAS, IoI16>;
-    v.real_i16 = fir16_block_kernel<C, float, MIN_CTAS, IoI16>;
-    v.persist_cplx = v.persist_real = nullptr;
-    v.shaped_cplx = fir16_block_kernel<C, cf, MIN_CTAS, IoF32, true>;
-    v.shaped_real = fir16_block_kernel<C, float, MIN_CTAS, IoF32, true>;
-    v.split_int_cplx = v.split_int_real = v.split_edge_cplx = v.split_edge_real = nullptr;
-    v.build = [](const float* mask, bool real_only, HostTables& out) {
-        out.tw1 = build16_tw1<C>();
-        out.tw2 = build16_tw2<C>();
-        build16_coef<C>(mask, real_only, out.coef_s, out.coef_x);
-    };
-    return v;
-}
-
-const FirVariant* all_variants(int* count) {
-    static const FirVariant table[] = {
-        make_variant32<FirCfg<16, 8>, 4>("p32"),   // N = 4096,  128 threads, 4 CTAs/SM
-        make_variant32<FirCfg<16, 16>, 2>("p32"),  // N = 8192,  256 threads, 2 CTAs/SM  (headline kernel)
-        make_variant32<FirCfg<16, 32>, 1>("p32"),  // N = 16384, 512 threads, 1 CTA/SM
-        make_variant16<Fir16Cfg<16>, 4>("p16"),    // N = 4096,  256 threads, <= 64 regs
-        make_variant16<Fir16Cfg<32>, 2>("p16"),    // N = 8192,  512 threads, <= 64 regs, 32 warps/SM
+const FirVariant* const* all_variants(int* count) {
+    static const FirVariant* table[] = {
+        fir_variant_p32_4096(),   // N = 4096,  128 threads, 4 CTAs/SM
+        fir_variant_p32_8192(),   // N = 8192,  256 threads, 2 CTAs/SM  (headline kernel)
+        fir_variant_p32_16384(),  // N = 16384, 512 threads, 1 CTA/SM
+        fir_variant_p16_4096(),   // A/B family, null unless built with AB=1
+        fir_variant_p16_8192(),
     };
     *count = (int)(sizeof table / sizeof table[0]);
     return table;
@@ -155,12 +85,12 @@ const FirVariant* all_variants(int* count) {
 
 const FirVariant* find_variant(int n, const char* name = nullptr) {
     int cnt = 0;
-    const FirVariant* t = all_variants(&cnt);
+    const FirVariant* const* t = all_variants(&cnt);
     if (name && *name)
         for (int i = 0; i < cnt; ++i)
-            if (t[i].n == n && !strcmp(t[i].name, name)) return &t[i];
+            if (t[i] && t[i]->n == n && !strcmp(t[i]->name, name)) return t[i];
     for (int i = 0; i < cnt; ++i)
-        if (t[i].n == n) return &t[i];
+        if (t[i] && t[i]->n == n) return t[i];
     return nullptr;
 }
 
@@ -193,9 +123,10 @@ extern "C" int adt_ctx_create(int device, adt_ctx** out) {
         return ADT_ERR_CUDA;
     }
     int n_var = 0;
-    const FirVariant* vars = all_variants(&n_var);
+    const FirVariant* const* vars = all_variants(&n_var);
     for (int vi = 0; vi < n_var; ++vi) {
-        const FirVariant* v = &vars[vi];
+        const FirVariant* v = vars[vi];
+        if (!v) continue;
         for (fir_kernel_fn f : {v->cplx, v->real, v->cplx_i16, v->real_i16, v->persist_cplx, v->persist_real,
                                 v->shaped_cplx, v->shaped_real, v->split_int_cplx, v->split_int_real,
                                 v->split_edge_cplx, v->split_edge_real}) {
@@ -248,6 +179,12 @@ extern "C" int adt_ctx_device_name(adt_ctx* ctx, char* buf, size_t len) {
     cudaDeviceProp p;
     CK(ctx, cudaGetDeviceProperties(&p, ctx->device));
     snprintf(buf, len, "%s (sm_%d%d, %d SMs)", p.name, p.major, p.minor, p.multiProcessorCount);
+    return ADT_OK;
+}
+
+extern "C" int adt_ctx_pci_bus_id(adt_ctx* ctx, char* buf, size_t len) {
+    if (!ctx || !buf || len < 13) return ADT_ERR_INVALID;
+    CK(ctx, cudaDeviceGetPCIBusId(buf, (int)len, ctx->device));
     return ADT_OK;
 }
 
@@ -427,7 +364,7 @@ static int fir_launch(adt_fir* f, cudaStream_t s, const void* x, int64_t in_pitc
     const int persist_mode = getenv("ADT_FIR_PERSIST") ? atoi(getenv("ADT_FIR_PERSIST")) : (f->d.fft_size == 16384);
     fir_kernel_fn kp = f->d.mask_is_real ? f->var->persist_real : f->var->persist_cplx;
     bool persistent = false;
-    if (persist_mode && !i16 && !shaped && kp && a.n_items >= 4LL * f->resident_ctas) {
+    if (persist_mode && !i16 && !shaped && kp && (persist_mode == 2 || a.n_items >= 4LL * f->resident_ctas)) {   // 2 = force (tests)
         if (!f->d_counter) CK(ctx, cudaMalloc((void**)&f->d_counter, (ADT_COPY_STREAMS + 1) * sizeof(unsigned int)));
         grid = (unsigned)f->resident_ctas;
         fir_set_counter<<<1, 1, 0, s>>>(f->d_counter + slot, grid);   // first unclaimed item = grid size

@@ -11,8 +11,10 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstring>
 #include <mutex>
 #include <new>
+#include <vector>
 
 #include "adt_internal.h"
 
@@ -127,52 +129,91 @@ extern "C" int adt_comm_destroy(adt_comm* c) {
     return ADT_OK;
 }
 
-extern "C" int adt_comm_scatter_rows(adt_comm* c, const float* full, float* shard, int64_t rows_per_rank, int64_t pitch,
-                                     int32_t root) {
-    if (!c || !shard || rows_per_rank < 0 || pitch < 0 || root < 0 || root >= c->world) return ADT_ERR_INVALID;
-    if (c->rank == root && !full) return ADT_ERR_INVALID;
+// Grouped point-to-point exchange between the root and every other rank.  `counts[r]` rows of `pitch` floats
+// belong to rank r, stored back to back in the root's matrix (offset = prefix sum).  to_root = false: scatter
+// (root sends), true: gather (root receives).  An error inside the group still closes the group before
+// returning, so a failed call never leaves NCCL waiting for ncclGroupEnd.
+static int comm_exchange_rows(adt_comm* c, const float* full_src, float* full_dst, const float* shard_src,
+                              float* shard_dst, const int64_t* counts, int64_t pitch, int32_t root, bool to_root) {
     adt_ctx* ctx = c->ctx;
     ADT_CK(ctx, cudaSetDevice(ctx->device));
-    const size_t count = (size_t)rows_per_rank * pitch;
-    if (count == 0) return ADT_OK;
-    NK(ctx, nccl().GroupStart());
-    if (c->rank == root) {
-        for (int r = 0; r < c->world; ++r) {
-            if (r == root) continue;
-            NK(ctx, nccl().Send(full + (size_t)r * count, count, ncclFloat, r, c->comm, ctx->stream));
-        }
-    } else {
-        NK(ctx, nccl().Recv(shard, count, ncclFloat, root, c->comm, ctx->stream));
+    int64_t my_off = 0, total = 0;
+    for (int r = 0; r < c->world; ++r) {
+        if (counts[r] < 0) return adt_set_error(ctx, ADT_ERR_INVALID, "negative row count for rank %d", r);
+        if (r < c->rank) my_off += counts[r];
+        total += counts[r];
     }
-    NK(ctx, nccl().GroupEnd());
-    if (c->rank == root)
-        ADT_CK(ctx, cudaMemcpyAsync(shard, full + (size_t)root * count, count * sizeof(float), cudaMemcpyDeviceToDevice,
-                                    ctx->stream));
+    if (total == 0 || pitch == 0) return ADT_OK;
+    const size_t mine = (size_t)counts[c->rank] * pitch;
+    ncclResult_t first = ncclSuccess;
+    const char* what = "";
+    auto note = [&](ncclResult_t r, const char* w) {
+        if (r != ncclSuccess && first == ncclSuccess) {
+            first = r;
+            what = w;
+        }
+    };
+    note(nccl().GroupStart(), "ncclGroupStart");
+    if (first == ncclSuccess) {
+        if (c->rank == root) {
+            int64_t off = 0;
+            for (int r = 0; r < c->world; ++r) {
+                const size_t n = (size_t)counts[r] * pitch;
+                if (r != root && n) {
+                    if (to_root)
+                        note(nccl().Recv(full_dst + (size_t)off * pitch, n, ncclFloat, r, c->comm, ctx->stream), "ncclRecv");
+                    else
+                        note(nccl().Send(full_src + (size_t)off * pitch, n, ncclFloat, r, c->comm, ctx->stream), "ncclSend");
+                }
+                off += counts[r];
+            }
+        } else if (mine) {
+            if (to_root)
+                note(nccl().Send(shard_src, mine, ncclFloat, root, c->comm, ctx->stream), "ncclSend");
+            else
+                note(nccl().Recv(shard_dst, mine, ncclFloat, root, c->comm, ctx->stream), "ncclRecv");
+        }
+        note(nccl().GroupEnd(), "ncclGroupEnd");   // always reached once the group was opened
+    }
+    if (first != ncclSuccess) return adt_set_error(ctx, ADT_ERR_NCCL, "%s: %s", what, nccl().GetErrorString(first));
+    if (c->rank == root && mine) {   // the root's own rows: a local copy on the same stream
+        if (to_root)
+            ADT_CK(ctx, cudaMemcpyAsync(full_dst + (size_t)my_off * pitch, shard_src, mine * sizeof(float),
+                                        cudaMemcpyDeviceToDevice, ctx->stream));
+        else
+            ADT_CK(ctx, cudaMemcpyAsync(shard_dst, full_src + (size_t)my_off * pitch, mine * sizeof(float),
+                                        cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     return ADT_OK;
+}
+
+extern "C" int adt_comm_scatterv_rows(adt_comm* c, const float* full, float* shard, const int64_t* row_counts,
+                                      int64_t pitch, int32_t root) {
+    if (!c || !row_counts || pitch < 0 || root < 0 || root >= c->world) return ADT_ERR_INVALID;
+    if ((c->rank == root && !full) || (!shard && row_counts[c->rank] > 0)) return ADT_ERR_INVALID;
+    return comm_exchange_rows(c, full, nullptr, nullptr, shard, row_counts, pitch, root, false);
+}
+
+extern "C" int adt_comm_gatherv_rows(adt_comm* c, const float* shard, float* full, const int64_t* row_counts,
+                                     int64_t pitch, int32_t root) {
+    if (!c || !row_counts || pitch < 0 || root < 0 || root >= c->world) return ADT_ERR_INVALID;
+    if ((c->rank == root && !full) || (!shard && row_counts[c->rank] > 0)) return ADT_ERR_INVALID;
+    return comm_exchange_rows(c, nullptr, full, shard, nullptr, row_counts, pitch, root, true);
+}
+
+// uniform shards: the same exchange with rows_per_rank everywhere
+extern "C" int adt_comm_scatter_rows(adt_comm* c, const float* full, float* shard, int64_t rows_per_rank, int64_t pitch,
+                                     int32_t root) {
+    if (!c || rows_per_rank < 0) return ADT_ERR_INVALID;
+    std::vector<int64_t> counts((size_t)c->world, rows_per_rank);
+    return adt_comm_scatterv_rows(c, full, shard, counts.data(), pitch, root);
 }
 
 extern "C" int adt_comm_gather_rows(adt_comm* c, const float* shard, float* full, int64_t rows_per_rank, int64_t pitch,
                                     int32_t root) {
-    if (!c || !shard || rows_per_rank < 0 || pitch < 0 || root < 0 || root >= c->world) return ADT_ERR_INVALID;
-    if (c->rank == root && !full) return ADT_ERR_INVALID;
-    adt_ctx* ctx = c->ctx;
-    ADT_CK(ctx, cudaSetDevice(ctx->device));
-    const size_t count = (size_t)rows_per_rank * pitch;
-    if (count == 0) return ADT_OK;
-    NK(ctx, nccl().GroupStart());
-    if (c->rank == root) {
-        for (int r = 0; r < c->world; ++r) {
-            if (r == root) continue;
-            NK(ctx, nccl().Recv(full + (size_t)r * count, count, ncclFloat, r, c->comm, ctx->stream));
-        }
-    } else {
-        NK(ctx, nccl().Send(shard, count, ncclFloat, root, c->comm, ctx->stream));
-    }
-    NK(ctx, nccl().GroupEnd());
-    if (c->rank == root)
-        ADT_CK(ctx, cudaMemcpyAsync(full + (size_t)root * count, shard, count * sizeof(float), cudaMemcpyDeviceToDevice,
-                                    ctx->stream));
-    return ADT_OK;
+    if (!c || rows_per_rank < 0) return ADT_ERR_INVALID;
+    std::vector<int64_t> counts((size_t)c->world, rows_per_rank);
+    return adt_comm_gatherv_rows(c, shard, full, counts.data(), pitch, root);
 }
 
 extern "C" int adt_comm_broadcast(adt_comm* c, void* buf, size_t bytes, int32_t root) {

@@ -1,0 +1,10 @@
+// fir_k4096.cu — kernels of the N = 4096 (128 threads, 4 CTAs/SM) transform (its own translation unit: sizes compile in parallel).
+#define ADT_FIR_VARIANT_IMPL
+#include "fir_variants.cuh"
+
+namespace adt {
+const FirVariant* fir_variant_p32_4096() {
+    static const FirVariant v = make_variant32<FirCfg<16, 8>, 4, false>("p32");
+    return &v;
+}
+}  // namespace adt

@@ -1,0 +1,10 @@
+// fir_k8192.cu — kernels of the N = 8192 (256 threads, 2 CTAs/SM; the headline kernel) transform (its own translation unit: sizes compile in parallel).
+#define ADT_FIR_VARIANT_IMPL
+#include "fir_variants.cuh"
+
+namespace adt {
+const FirVariant* fir_variant_p32_8192() {
+    static const FirVariant v = make_variant32<FirCfg<16, 16>, 2, false>("p32");
+    return &v;
+}
+}  // namespace adt

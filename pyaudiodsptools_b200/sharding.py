@@ -109,6 +109,20 @@ class Communicator:
     def gather_rows(self, shard_dev, full_dev, rows_per_rank, pitch, root=0):
         self.ctx.check(self.ctx.lib.adt_comm_gather_rows(self.h, shard_dev, full_dev, rows_per_rank, pitch, root))
 
+    def channel_counts(self, n_channels):
+        """Rows per rank of the documented partition (``channel_range``), as the int64 array the C ABI takes."""
+        counts = [b - a for a, b in (channel_range(n_channels, self.world, r) for r in range(self.world))]
+        return (C.c_int64 * self.world)(*counts)
+
+    def scatter_channels(self, full_dev, shard_dev, n_channels, pitch, root=0):
+        """Scatter the root's [n_channels][pitch] device matrix by ``channel_range`` (uneven shards allowed)."""
+        self.ctx.check(self.ctx.lib.adt_comm_scatterv_rows(self.h, full_dev, shard_dev, self.channel_counts(n_channels),
+                                                           pitch, root))
+
+    def gather_channels(self, shard_dev, full_dev, n_channels, pitch, root=0):
+        self.ctx.check(self.ctx.lib.adt_comm_gatherv_rows(self.h, shard_dev, full_dev, self.channel_counts(n_channels),
+                                                          pitch, root))
+
     def broadcast(self, buf_dev, nbytes, root=0):
         self.ctx.check(self.ctx.lib.adt_comm_broadcast(self.h, buf_dev, nbytes, root))
 

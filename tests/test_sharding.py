@@ -82,6 +82,23 @@ if rank == 0:
     for ch in (0, per - 1, per, world * per - 1):
         want = oracle.fir_stream_f64(taps, c, full[ch])
         assert np.sqrt(np.mean((y[ch] - want) ** 2)) < 2e-6, ch
+# uneven shards: 2*world + 3 channels split by channel_range (pairs never straddle), scatterv / gatherv
+n_ch = 2 * world + 3
+lo, hi = sharding.channel_range(n_ch, world, rank)
+full2 = np.random.default_rng(1).uniform(-1, 1, (n_ch, n)).astype(np.float32)
+d_f2 = ctx.malloc(full2.nbytes); d_i2 = ctx.malloc(max(hi - lo, 1) * n * 4); d_o2 = ctx.malloc(max(hi - lo, 1) * n * 4)
+if rank == 0: ctx.h2d(d_f2, full2)
+comm.scatter_channels(d_f2, d_i2, n_ch, n, root=0)
+if hi > lo:
+    dev2 = adt.CreateLowCutFilter(800, channels=hi - lo, device=rank)
+    dev2.process_device(d_i2, n, n, d_o2, n, n, hi - lo)
+comm.gather_channels(d_o2, d_f2, n_ch, n, root=0)
+comm.barrier()
+if rank == 0:
+    y2 = np.empty_like(full2); ctx.d2h(y2, d_f2)
+    for ch in range(n_ch):
+        want = oracle.fir_stream_f64(taps, c, full2[ch])
+        assert np.sqrt(np.mean((y2[ch] - want) ** 2)) < 2e-6, ("uneven", ch)
 comm.close()
 dist.destroy_process_group()
 print("rank", rank, "nccl ok")
@@ -91,12 +108,15 @@ print("rank", rank, "nccl ok")
 @pytest.mark.gpu
 def test_nccl_scatter_filter_gather(tmp_path):
     from pyaudiodsptools_b200 import _native
-    if _native.device_count() < 2:
-        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    n_gpus = _native.device_count()
+    if n_gpus < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2); logs of the 2- and 8-GPU runs: profiles/r02_nccl_*.log")
+    world = int(os.environ.get("ADT_TEST_WORLD", "0")) or min(n_gpus, 8)
     script = tmp_path / "n.py"
     script.write_text(_NCCL_WORKER.format(root=ROOT))
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                         "--master-addr", "127.0.0.1", "--master-port", "29614", str(script)],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("nccl ok") == 2
+    assert r.stdout.count("nccl ok") == world
+    print(r.stdout[-1500:])
