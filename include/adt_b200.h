@@ -162,6 +162,14 @@ int adt_biquad_reset(adt_biquad* bq);
 /* rows of n samples; element type float (f64 == 0) or double (f64 == 1) */
 int adt_biquad_apply_dev(adt_biquad* bq, const void* x_dev, void* y_dev, int64_t pitch, int64_t n);
 int adt_biquad_apply_host(adt_biquad* bq, const void* x_host, void* y_host, int64_t pitch, int64_t n);
+/* applyhighband(applymidband(applylowband(x))) in ONE launch: the three bands run as a software pipeline over
+ * 32-sample time tiles (one warp per band, tiles handed over in shared memory), so the sequential recurrence
+ * is walked once instead of three times.  Same individually rounded arithmetic per band -> bit-identical to
+ * the three separate calls; each band's own state is read and updated, so both styles can be mixed. */
+int adt_biquad_chain_apply_dev(adt_biquad* low, adt_biquad* mid, adt_biquad* high, const void* x_dev, void* y_dev,
+                               int64_t pitch, int64_t n);
+int adt_biquad_chain_apply_host(adt_biquad* low, adt_biquad* mid, adt_biquad* high, const void* x_host, void* y_host,
+                                int64_t pitch, int64_t n);
 
 /* ---- channel sharding across the GPUs of one box (NCCL over NVLink) ---------
  * Channels are independent, so the only exchanges are a scatter of input rows

@@ -76,6 +76,8 @@ PROTOTYPES = {
     "adt_biquad_reset": (C.c_int, [_P]),
     "adt_biquad_apply_dev": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64]),
     "adt_biquad_apply_host": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64]),
+    "adt_biquad_chain_apply_dev": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64]),
+    "adt_biquad_chain_apply_host": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64]),
     "adt_comm_unique_id": (C.c_int, [C.c_char_p]),
     "adt_comm_create": (C.c_int, [_P, C.c_char_p, C.c_int32, C.c_int32, C.POINTER(_P)]),
     "adt_comm_destroy": (C.c_int, [_P]),

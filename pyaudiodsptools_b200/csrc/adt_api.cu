@@ -129,7 +129,7 @@ extern "C" int adt_ctx_create(int device, adt_ctx** out) {
         if (!v) continue;
         for (fir_kernel_fn f : {v->cplx, v->real, v->cplx_i16, v->real_i16, v->persist_cplx, v->persist_real,
                                 v->shaped_cplx, v->shaped_real, v->split_int_cplx, v->split_int_real,
-                                v->split_edge_cplx, v->split_edge_real}) {
+                                v->split_edge_cplx, v->split_edge_real, v->tma_cplx, v->tma_real}) {
             if (!f) continue;
             e = cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->smem);
             if (e == cudaSuccess && getenv("ADT_FIR_CARVEOUT"))  // tuning knob: % of the 228 KB given to shared memory
@@ -349,6 +349,8 @@ static int fir_launch(adt_fir* f, cudaStream_t s, const void* x, int64_t in_pitc
                              : (f->d.mask_is_real ? f->var->real : f->var->cplx);
     if (a.n_items > 0x7fffffffLL)
         return adt_set_error(ctx, ADT_ERR_UNSUPPORTED, "too many work items: %lld", (long long)a.n_items);
+    static const int tma_mode = getenv("ADT_FIR_TMA") ? atoi(getenv("ADT_FIR_TMA")) : 0;   // A/B: TMA-fed window load
+    if (tma_mode && !shaped && !i16 && f->var->tma_real) k = f->d.mask_is_real ? f->var->tma_real : f->var->tma_cplx;
     if (f->resident_ctas == 0) {  // CTAs in flight at once = how far ahead the L2 prefetch looks
         int per_sm = 0, sms = 0;
         CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, f->var->threads, f->var->smem));

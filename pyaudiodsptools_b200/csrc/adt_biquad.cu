@@ -17,9 +17,14 @@
 // makes the result bit-identical to the reference, not merely close.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <new>
 
 #include "adt_internal.h"
+
+#ifndef ADT_BIQUAD_ROUND_INT_DEFAULT
+#define ADT_BIQUAD_ROUND_INT_DEFAULT 0   /* set from the measurement in tools/microbench/lat64.cu */
+#endif
 
 namespace {
 
@@ -91,6 +96,127 @@ __global__ void __launch_bounds__(32) biquad_kernel(const T* __restrict__ x, T* 
     }
     if (live) {
         double* s = state + (long long)ch * 5;
+        s[0] = x1; s[1] = x2; s[2] = x3; s[3] = y1; s[4] = y2;
+    }
+}
+
+
+// ---- low -> mid -> high chain in ONE launch -----------------------------------------------------------
+// The recurrence leaves exactly one unit of parallelism per (channel, band): a dependent chain
+// DMUL -> DADD -> DADD -> round-to-float32 per sample.  Three separate band launches walk that chain three
+// times back to back; here the three bands of a 32-channel tile run CONCURRENTLY as a software pipeline over
+// time tiles: warp b filters tile (step - b) with band b, handing tiles to the next warp through double-
+// buffered shared memory, so the chain is walked once (+2 tiles of fill).  Arithmetic per band is the same
+// individually rounded sequence as biquad_kernel, so the result stays bit-identical to
+// applyhighband(applymidband(applylowband(x))).
+//
+// ROUND_INT: round the float64 accumulator to float32 precision by integer arithmetic on the bit pattern
+// (round-to-nearest-even on the 29 dropped mantissa bits; the carry propagates into the exponent exactly as
+// IEEE rounding does) instead of the F2F.F32.F64 / F2F.F64.F32 pair.  Identical results for every value whose
+// float32 image is a normal number; values below 2^-126 (float32 denormals), infinities and NaNs take the
+// conversion path, so the result is bit-exact everywhere.  Measured: tools/microbench/lat64.cu.
+struct Biquad3Args {
+    BiquadCoef k[3];
+    double* state[3];
+};
+
+template <typename T, bool ROUND_INT>
+struct BiquadRound;
+template <bool ROUND_INT>
+struct BiquadRound<double, ROUND_INT> {
+    static __device__ __forceinline__ double run(double acc, double* out) { *out = acc; return acc; }
+};
+template <>
+struct BiquadRound<float, false> {
+    static __device__ __forceinline__ double run(double acc, float* out) {
+        const float f = __double2float_rn(acc);
+        *out = f;
+        return (double)f;
+    }
+};
+template <>
+struct BiquadRound<float, true> {
+    static __device__ __forceinline__ double run(double acc, float* out) {
+        long long b = __double_as_longlong(acc);
+        const unsigned e = ((unsigned)(b >> 52)) & 0x7ffu;              // biased float64 exponent
+        if (e - 897u >= 1150u - 897u) {   // outside [2^-126, 2^127): zero, float32-denormal, huge, inf, nan
+            const float f = __double2float_rn(acc);
+            *out = f;
+            return (double)f;
+        }
+        b += 0x0FFFFFFFLL + ((b >> 29) & 1);
+        b &= ~0x1FFFFFFFLL;
+        const double r = __longlong_as_double(b);
+        *out = __double2float_rn(r);      // exact (already float32-representable) and off the dependent chain
+        return r;
+    }
+};
+
+template <typename T, bool ROUND_INT>
+__global__ void __launch_bounds__(96) biquad3_kernel(const T* __restrict__ x, T* __restrict__ y, long long pitch,
+                                                     long long n, int n_channels, Biquad3Args a) {
+    extern __shared__ __align__(16) unsigned char bq_smem[];
+    typedef T Tile[32][33];
+    Tile* tiles = reinterpret_cast<Tile*>(bq_smem);   // [0] input, [1..2] low->mid, [3..4] mid->high, [5] output
+    const int lane = threadIdx.x & 31, band = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * 32;
+    const int ch = c0 + lane;
+    const bool live = ch < n_channels;
+    const int rows = min(32, n_channels - c0);
+    const BiquadCoef k = a.k[band];
+    double x1 = 0, x2 = 0, x3 = 0, y1 = 0, y2 = 0;
+    if (live) {
+        const double* s = a.state[band] + (long long)ch * 5;
+        x1 = s[0]; x2 = s[1]; x3 = s[2]; y1 = s[3]; y2 = s[4];
+    }
+    const long long n_tiles = (n + 31) / 32;
+    const T* xr = x + (long long)c0 * pitch + lane;
+    T* yr = y + (long long)c0 * pitch + lane;
+    T nxt[32];
+    if (band == 0) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) nxt[i] = (i < rows && lane < n) ? xr[(long long)i * pitch] : T(0);
+    }
+    for (long long step = 0; step < n_tiles + 2; ++step) {
+        const long long tile = step - band;
+        const bool active = tile >= 0 && tile < n_tiles;
+        const long long base = tile * 32;
+        const int w = active ? (int)min((long long)32, n - base) : 0;
+        Tile& src = band == 0 ? tiles[0] : tiles[(band == 1 ? 1 : 3) + (int)(tile & 1)];
+        Tile& dst = band == 2 ? tiles[5] : tiles[(band == 0 ? 1 : 3) + (int)(tile & 1)];
+        if (band == 0 && active) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) src[i][lane] = nxt[i];
+            __syncwarp();
+            const long long nb = base + 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) nxt[i] = (i < rows && nb + lane < n) ? xr[(long long)i * pitch + nb] : T(0);
+        }
+        if (active && live) {
+            for (int j = 0; j < w; ++j) {
+                const double xin = (double)src[lane][j];
+                double acc = __dmul_rn(k.c[0], x1);
+                acc = __dadd_rn(acc, __dmul_rn(k.c[1], x2));
+                acc = __dadd_rn(acc, __dmul_rn(k.c[2], x3));
+                acc = __dsub_rn(acc, __dmul_rn(k.c[3], y1));
+                acc = __dsub_rn(acc, __dmul_rn(k.c[4], y2));
+                T out;
+                const double fb = BiquadRound<T, ROUND_INT>::run(acc, &out);
+                dst[lane][j] = out;
+                x3 = x2; x2 = x1; x1 = xin;
+                y2 = y1; y1 = fb;
+            }
+        }
+        if (band == 2 && active) {
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (i < rows && lane < w) yr[(long long)i * pitch + base] = dst[i][lane];
+        }
+        __syncthreads();   // hand the tiles over: band b's output of this step is band b+1's input of the next
+    }
+    if (live) {
+        double* s = a.state[band] + (long long)ch * 5;
         s[0] = x1; s[1] = x2; s[2] = x3; s[3] = y1; s[4] = y2;
     }
 }
@@ -187,6 +313,77 @@ extern "C" int adt_biquad_apply_host(adt_biquad* b, const void* x, void* y, int6
     int rc = adt_biquad_apply_dev(b, b->d_x, b->d_y, n, n);
     if (rc) return rc;
     ADT_CK(ctx, cudaMemcpy2DAsync(y, pitch * es, b->d_y, n * es, n * es, b->n_channels, cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    ADT_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return ADT_OK;
+}
+
+// low -> mid -> high in one launch; each band keeps its own coefficients and state (the three adt_biquad
+// objects of one CreateEQ3Band), so chained and per-band calls can be mixed freely.
+extern "C" int adt_biquad_chain_apply_dev(adt_biquad* low, adt_biquad* mid, adt_biquad* high, const void* x, void* y,
+                                          int64_t pitch, int64_t n) {
+    if (!low || !mid || !high || !x || !y || n < 0 || pitch < n) return ADT_ERR_INVALID;
+    adt_ctx* ctx = low->ctx;
+    if (mid->ctx != ctx || high->ctx != ctx || mid->n_channels != low->n_channels || high->n_channels != low->n_channels ||
+        mid->f64 != low->f64 || high->f64 != low->f64)
+        return adt_set_error(ctx, ADT_ERR_INVALID, "the three bands of a chain must share context, channel count and dtype");
+    if (n == 0) return ADT_OK;
+    ADT_CK(ctx, cudaSetDevice(ctx->device));
+    Biquad3Args a;
+    adt_biquad* b[3] = {low, mid, high};
+    for (int i = 0; i < 3; ++i) {
+        a.k[i] = b[i]->k;
+        a.state[i] = b[i]->d_state;
+    }
+    const unsigned grid = (unsigned)((low->n_channels + 31) / 32);
+    static const int round_int = getenv("ADT_BIQUAD_ROUND_INT") ? atoi(getenv("ADT_BIQUAD_ROUND_INT")) : ADT_BIQUAD_ROUND_INT_DEFAULT;
+    if (low->f64) {
+        const size_t smem = 6 * 32 * 33 * sizeof(double);
+        static bool attr_done = false;
+        if (!attr_done) {
+            ADT_CK(ctx, cudaFuncSetAttribute((const void*)biquad3_kernel<double, false>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_done = true;
+        }
+        biquad3_kernel<double, false><<<grid, 96, smem, ctx->stream>>>((const double*)x, (double*)y, pitch, n,
+                                                                      low->n_channels, a);
+    } else {
+        const size_t smem = 6 * 32 * 33 * sizeof(float);
+        if (round_int)
+            biquad3_kernel<float, true><<<grid, 96, smem, ctx->stream>>>((const float*)x, (float*)y, pitch, n,
+                                                                        low->n_channels, a);
+        else
+            biquad3_kernel<float, false><<<grid, 96, smem, ctx->stream>>>((const float*)x, (float*)y, pitch, n,
+                                                                         low->n_channels, a);
+    }
+    ADT_CK(ctx, cudaGetLastError());
+    ctx->launches++;
+    return ADT_OK;
+}
+
+extern "C" int adt_biquad_chain_apply_host(adt_biquad* low, adt_biquad* mid, adt_biquad* high, const void* x, void* y,
+                                           int64_t pitch, int64_t n) {
+    if (!low || !mid || !high || !x || !y || n < 0 || pitch < n) return ADT_ERR_INVALID;
+    adt_ctx* ctx = low->ctx;
+    if (n == 0) return ADT_OK;
+    ADT_CK(ctx, cudaSetDevice(ctx->device));
+    const size_t es = low->f64 ? sizeof(double) : sizeof(float);
+    const size_t need = (size_t)low->n_channels * n * es;
+    if (low->cap < need) {
+        ADT_CK(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(low->d_x);
+        cudaFree(low->d_y);
+        low->d_x = low->d_y = nullptr;
+        low->cap = 0;
+        ADT_CK(ctx, cudaMalloc(&low->d_x, need));
+        ADT_CK(ctx, cudaMalloc(&low->d_y, need));
+        low->cap = need;
+    }
+    ADT_CK(ctx, cudaMemcpy2DAsync(low->d_x, n * es, x, pitch * es, n * es, low->n_channels, cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    int rc = adt_biquad_chain_apply_dev(low, mid, high, low->d_x, low->d_y, n, n);
+    if (rc) return rc;
+    ADT_CK(ctx, cudaMemcpy2DAsync(y, pitch * es, low->d_y, n * es, n * es, low->n_channels, cudaMemcpyDeviceToHost,
                                   ctx->stream));
     ADT_CK(ctx, cudaStreamSynchronize(ctx->stream));
     return ADT_OK;

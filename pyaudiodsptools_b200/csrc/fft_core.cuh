@@ -93,18 +93,36 @@ ADT_HD cf mul_s(float s, cf w) {
     return mk(s * w.x, s * w.y);
 #endif
 }
-// a*b = a.x*(b.x, b.y) + a.y*(-b.y, b.x)
-ADT_HD cf cmul(cf a, cf b) { return fma_s(a.x, b, mul_s(a.y, mk(-b.y, b.x))); }
-// a * conj(b) = a.x*(b.x, -b.y) + a.y*(b.y, b.x)
-ADT_HD cf cmulc(cf a, cf b) { return fma_s(a.x, mk(b.x, -b.y), mul_s(a.y, mk(b.y, b.x))); }
+// pair * broadcast scalar (+ pair), with the PAIR as the first operand: ptxas folds a half swap and a
+// per-half sign flip of the first operand into the instruction (SASS `-R.F32x2.LO_HI.NP`), but only there —
+// written the other way round (scalar first, swizzled pair second) it materialises the swizzled pair with a
+// MOV + FADD per use (round 1: 90 FADD + ~130 MOV per thread in the headline kernel).
+ADT_HD cf pmul_s(cf w, float s) {
+#if defined(__CUDA_ARCH__)
+    return __fmul2_rn(w, mk(s, s));
+#else
+    return mk(w.x * s, w.y * s);
+#endif
+}
+ADT_HD cf pfma_s(cf w, float s, cf acc) {
+#if defined(__CUDA_ARCH__)
+    return __ffma2_rn(w, mk(s, s), acc);
+#else
+    return mk(w.x * s + acc.x, w.y * s + acc.y);
+#endif
+}
+// a*b = b.x*(a.x, a.y) + b.y*(-a.y, a.x)        (2 packed instructions)
+ADT_HD cf cmul(cf a, cf b) { return pfma_s(a, b.x, pmul_s(mk(-a.y, a.x), b.y)); }
+// a * conj(b) = b.x*(a.x, a.y) + b.y*(a.y, -a.x)
+ADT_HD cf cmulc(cf a, cf b) { return pfma_s(a, b.x, pmul_s(mk(a.y, -a.x), b.y)); }
 // acc + a*b
-ADT_HD cf cfma(cf a, cf b, cf acc) { return fma_s(a.x, b, fma_s(a.y, mk(-b.y, b.x), acc)); }
+ADT_HD cf cfma(cf a, cf b, cf acc) { return pfma_s(a, b.x, pfma_s(mk(-a.y, a.x), b.y, acc)); }
 
 ADT_HD cf mask_mul(cf a, float h) { return mul_s(h, a); }  // zero-phase (real) mask
 ADT_HD cf mask_mul(cf a, cf h) { return cmul(a, h); }
 // acc + a*h
 ADT_HD cf mask_fma(cf a, float h, cf acc) { return fma_s(h, a, acc); }
-ADT_HD cf mask_fma(cf a, cf h, cf acc) { return fma_s(a.x, h, fma_s(a.y, mk(-h.y, h.x), acc)); }
+ADT_HD cf mask_fma(cf a, cf h, cf acc) { return cfma(a, h, acc); }
 
 // cos / sin of 2*pi*q/32 as literals (constexpr trig is not available).
 ADT_HD constexpr float cos32(int q) {
@@ -245,7 +263,7 @@ ADT_HD void apply_powers(cf* v, cf w1) {
 }
 
 // acc + x * conj(p)
-ADT_HD cf cfmac(cf x, cf p, cf acc) { return fma_s(x.x, mk(p.x, -p.y), fma_s(x.y, mk(p.y, p.x), acc)); }
+ADT_HD cf cfmac(cf x, cf p, cf acc) { return pfma_s(x, p.x, pfma_s(mk(x.y, -x.x), p.y, acc)); }
 
 // v[k] *= conj(w1^k) followed by the inverse R-point DFT, with the twiddles FOLDED into the first
 // radix-2 stage: that stage pairs (v[j], v[j+R/2]) with unit twiddle, so

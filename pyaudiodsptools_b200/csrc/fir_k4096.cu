@@ -4,7 +4,7 @@
 
 namespace adt {
 const FirVariant* fir_variant_p32_4096() {
-    static const FirVariant v = make_variant32<FirCfg<16, 8>, 4, false>("p32");
+    static const FirVariant v = make_variant32<FirCfg<16, 8>, 4, false, true>("p32");
     return &v;
 }
 }  // namespace adt

@@ -4,7 +4,7 @@
 
 namespace adt {
 const FirVariant* fir_variant_p32_8192() {
-    static const FirVariant v = make_variant32<FirCfg<16, 16>, 2, false>("p32");
+    static const FirVariant v = make_variant32<FirCfg<16, 16>, 2, false, true>("p32");
     return &v;
 }
 }  // namespace adt

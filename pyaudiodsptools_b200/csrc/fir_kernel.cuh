@@ -119,6 +119,69 @@ __global__ void __launch_bounds__(C::T, MIN_CTAS) fir_block_kernel(const FirKern
     store_slice<C, IO, SHAPED>(v, t, it.ya, it.yb, it.m0, a.g, ex.shape);
 }
 
+// TMA-FED variant (A/B, ADT_FIR_TMA=1): the two row windows of an interior item are brought
+// into the (not yet used) tile by the bulk-copy engine — one cp.async.bulk.shared::cluster.global per row,
+// completion on an mbarrier (SASS: UBLKCP + SYNCS) — and stage 1 reads its 32 points from shared memory
+// instead of issuing 64 LDG.32.  Costs two extra block barriers (mbarrier init visible; all reads done before
+// stage 1 overwrites the tile) and keeps the same number of L1 wavefronts (64 LDS.32 replace 64 LDG.32).
+// Edge items (window crossing the ends of the row, odd last row, rows not 16-byte aligned) use the LDG path.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+template <class C, class MaskT, int MIN_CTAS>
+__global__ void __launch_bounds__(C::T, MIN_CTAS) fir_tma_kernel(const FirKernelArgs a, const FirExtra ex) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cf* tile = reinterpret_cast<cf*>(smem_raw);
+    __shared__ __align__(8) unsigned long long bar;
+    const int t = threadIdx.x;
+    const long long item = blockIdx.x;
+    const FirItem<float> it = fir_item<float>(a, item);
+    cf v[32];
+    const bool bulk = it.xb && it.ws >= 0 && it.ws + C::N <= a.g.n_in &&
+                      ((((unsigned long long)(it.xa + it.ws)) | ((unsigned long long)(it.xb + it.ws))) & 15ull) == 0;
+    if (bulk) {
+        float* sa = reinterpret_cast<float*>(smem_raw);
+        float* sb = sa + C::N;
+        constexpr unsigned BYTES = C::N * sizeof(float);
+        if (t == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(2 * BYTES) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(sa)), "l"(it.xa + it.ws), "r"(BYTES), "r"(smem_u32(&bar)) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(sb)), "l"(it.xb + it.ws), "r"(BYTES), "r"(smem_u32(&bar)) : "memory");
+        }
+        fir_prefetch_l2<C::N, C::T, float>(a, item, t);
+        __syncthreads();                                  // the initialised barrier is visible to every waiter
+        unsigned done = 0;
+        while (!done) {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done) : "r"(smem_u32(&bar)) : "memory");
+        }
+        static_for<0, C::B1>([&](auto U) {
+            static_for<0, C::N1>([&](auto K) {
+                constexpr int u = decltype(U)::value, n1 = decltype(K)::value;
+                constexpr int s = n1 * C::M1 + u * C::T;
+                v[u * C::N1 + n1] = mk(sa[s + t], sb[s + t]);
+            });
+        });
+        __syncthreads();                                  // every point is in registers before stage 1 reuses the tile
+    } else {
+        load_window<C, IoF32>(v, t, it.xa, it.xb, it.ws, a.g.n_in);
+        fir_prefetch_l2<C::N, C::T, float>(a, item, t);
+    }
+    fwd_stage1<C>(v, t, a.tw1, tile);
+    __syncthreads();
+    fwd_stage2<C>(v, t, a.tw2, tile);
+    __syncwarp();
+    mid_stage3<C, MaskT>(v, t, reinterpret_cast<const MaskT*>(a.mask), tile);
+    __syncwarp();
+    inv_stage2<C>(v, t, a.tw2, tile);
+    __syncthreads();
+    inv_stage1<C>(v, t, a.tw1, tile);
+    store_slice<C, IoF32, false>(v, t, it.ya, it.yb, it.m0, a.g, ex.shape);
+}
+
 // PERSISTENT variant with a DYNAMIC work queue: the grid is one wave of resident CTAs; each CTA claims
 // items from an atomic counter (a static stride would pace the kernel by the slowest SM — measured 15 %
 // slower).  No barrier is needed between items because every tile exchange is in place, so warps flow

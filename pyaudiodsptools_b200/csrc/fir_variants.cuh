@@ -32,12 +32,13 @@ struct FirVariant {
     fir_kernel_fn persist_cplx, persist_real;  // persistent dynamic-queue variant (p32, float32 I/O) or null
     fir_kernel_fn shaped_cplx, shaped_real;    // float32 I/O with the wave-shaper store epilogue
     fir_kernel_fn split_int_cplx, split_int_real, split_edge_cplx, split_edge_real;  // split launch (p32) or null
+    fir_kernel_fn tma_cplx, tma_real;          // TMA-fed window load (A/B, ADT_FIR_TMA=1) or null
     void (*build)(const float* mask, bool real_only, HostTables& out);
 };
 
 #ifdef ADT_FIR_VARIANT_IMPL
 // 32 points per thread (fft_core.cuh).  PERSIST: also build the persistent dynamic-queue kernel.
-template <class C, int MIN_CTAS, bool PERSIST>
+template <class C, int MIN_CTAS, bool PERSIST, bool TMA = false>
 FirVariant make_variant32(const char* name) {
     FirVariant v;
     v.name = name;
@@ -56,6 +57,11 @@ FirVariant make_variant32(const char* name) {
     v.shaped_cplx = fir_block_kernel<C, cf, MIN_CTAS, IoF32, true>;
     v.shaped_real = fir_block_kernel<C, float, MIN_CTAS, IoF32, true>;
     v.split_int_cplx = v.split_int_real = v.split_edge_cplx = v.split_edge_real = nullptr;
+    v.tma_cplx = v.tma_real = nullptr;
+    if constexpr (TMA) {
+        v.tma_cplx = fir_tma_kernel<C, cf, MIN_CTAS>;
+        v.tma_real = fir_tma_kernel<C, float, MIN_CTAS>;
+    }
 #if ADT_AB_VARIANTS
     v.split_int_cplx = fir_split_kernel<C, cf, MIN_CTAS, true>;
     v.split_int_real = fir_split_kernel<C, float, MIN_CTAS, true>;
@@ -86,6 +92,7 @@ FirVariant make_variant16(const char* name) {
     v.shaped_cplx = fir16_block_kernel<C, cf, MIN_CTAS, IoF32, true>;
     v.shaped_real = fir16_block_kernel<C, float, MIN_CTAS, IoF32, true>;
     v.split_int_cplx = v.split_int_real = v.split_edge_cplx = v.split_edge_real = nullptr;
+    v.tma_cplx = v.tma_real = nullptr;
     v.build = [](const float* mask, bool real_only, HostTables& out) {
         out.tw1 = build16_tw1<C>();
         out.tw2 = build16_tw2<C>();

@@ -375,3 +375,45 @@ def test_biquad_batched_channels(gpu_lib):
         o = oracle.Eq3BandBiquad(100, 2, 700, -4, 8000, 5)
         want = np.concatenate([o.applymidband(x[ch, :n].copy()), o.applymidband(x[ch, n:].copy())])
         np.testing.assert_array_equal(y[ch], want)
+
+
+@pytest.mark.parametrize("round_int", ["0", "1"])
+def test_biquad_fused_chain_equals_three_launches(gpu_lib, round_int, tmp_path):
+    """The one-launch low->mid->high pipeline is bit-identical to the three per-band launches (and to the
+    oracle), shares their state, handles ragged tiles / channel counts, both rounding implementations, and
+    float32 denormals (a decaying tail crosses 2^-126, where the integer rounding hands over to F2F)."""
+    import os, subprocess, sys
+    from conftest import ROOT
+    script = tmp_path / "b.py"
+    script.write_text(f"""
+import sys
+sys.path.insert(0, {ROOT!r})
+import numpy as np
+import oracle
+import pyaudiodsptools_b200 as adt
+chans, n = 70, 1517
+rng = np.random.default_rng(21)
+x = rng.uniform(-1, 1, (chans, 3 * n)).astype(np.float32)
+x[:, n:] *= 1e-36                      # outputs decay through the float32 denormal range
+x[:, 2 * n:] = 0
+a = adt.CreateEQ3Band(100, 2, 700, -4, 8000, 5, channels=chans)
+b = adt.CreateEQ3Band(100, 2, 700, -4, 8000, 5, channels=chans)
+for i in range(3):
+    blk = x[:, i * n:(i + 1) * n]
+    ya = a.apply(blk)
+    yb = b.applyhighband(b.applymidband(b.applylowband(blk)))
+    assert np.array_equal(ya.view(np.uint32), yb.view(np.uint32)), i
+o = oracle.Eq3BandBiquad(100, 2, 700, -4, 8000, 5)
+c = adt.CreateEQ3Band(100, 2, 700, -4, 8000, 5, channels=chans)
+y = np.concatenate([c.apply(x[:, :n]), c.applymidband(x[:, n:2 * n])], axis=1)     # mixed styles share state
+want = np.concatenate([o.applyhighband(o.applymidband(o.applylowband(x[69, :n].copy()))), o.applymidband(x[69, n:2 * n].copy())])
+assert np.array_equal(y[69], want)
+xd = rng.uniform(-1, 1, (3, 500))
+d = adt.CreateEQ3Band(100, 2, 700, -4, 8000, 5, channels=3)
+od = oracle.Eq3BandBiquad(100, 2, 700, -4, 8000, 5)
+assert np.array_equal(d.apply(xd)[2], od.applyhighband(od.applymidband(od.applylowband(xd[2].copy()))))
+print("fused chain ok")
+""")
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, ADT_BIQUAD_ROUND_INT=round_int))
+    assert r.returncode == 0 and "fused chain ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

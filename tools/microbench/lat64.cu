@@ -1,0 +1,72 @@
+// Dependent-chain latencies that bound the bit-exact biquad recurrence (adt_biquad.cu) on sm_100a:
+// DMUL, DADD, DFMA, the float64 -> float32 -> float64 rounding round trip, an integer emulation of that
+// rounding, and the full per-sample step.  One warp, clock64() around a chain of N dependent operations.
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#define N 4096
+__device__ __forceinline__ double round32_int(double v) {
+    // round-to-nearest-even of a double to 24 significant bits by integer arithmetic on the bit pattern
+    // (valid for float32-normal magnitudes; denormal / overflow ranges need the F2F path)
+    long long b = __double_as_longlong(v);
+    b += 0x0FFFFFFFLL + ((b >> 29) & 1);
+    b &= ~0x1FFFFFFFLL;
+    return __longlong_as_double(b);
+}
+
+template <int MODE>
+__global__ void k(double* out, double a, double b, int lanes) {
+    if ((int)threadIdx.x >= lanes) return;
+    double y1 = a * threadIdx.x + 0.1, y2 = 0.3, acc = 0.7;
+    long long t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < N; ++i) {
+        if (MODE == 0) y1 = __dmul_rn(y1, b);
+        if (MODE == 1) y1 = __dadd_rn(y1, b);
+        if (MODE == 2) y1 = __fma_rn(y1, b, a);
+        if (MODE == 3) y1 = (double)__double2float_rn(y1 + 0.0) ;          // F2F.F32.F64 + F2F.F64.F32 (+ a DADD so it is not folded)
+        if (MODE == 4) y1 = round32_int(__dadd_rn(y1, b));
+        if (MODE == 5) {   // the biquad step: chain = DMUL, DADD, DADD, round trip
+            double t = __dsub_rn(acc, __dmul_rn(b, y1));
+            t = __dsub_rn(t, __dmul_rn(a, y2));
+            y2 = y1;
+            y1 = (double)__double2float_rn(t);
+        }
+        if (MODE == 6) {   // same with the integer rounding
+            double t = __dsub_rn(acc, __dmul_rn(b, y1));
+            t = __dsub_rn(t, __dmul_rn(a, y2));
+            y2 = y1;
+            y1 = round32_int(t);
+        }
+        if (MODE == 7) y1 = (double)(float)((float)y1 * 1.0001f);            // FMUL + conversions, for comparison
+    }
+    long long t1 = clock64();
+    out[threadIdx.x] = y1 + y2;
+    if (threadIdx.x == 0) out[64] = (double)(t1 - t0) / N;
+}
+
+template <int MODE>
+void run(const char* name, double* d) {
+    for (int lanes : {32, 8, 1}) {
+        k<MODE><<<1, 32>>>(d, 0.999, 0.5, lanes);
+        cudaDeviceSynchronize();
+        k<MODE><<<1, 32>>>(d, 0.999, 0.5, lanes);
+        double h;
+        cudaMemcpy(&h, d + 64, sizeof h, cudaMemcpyDeviceToHost);
+        printf("%-52s lanes=%2d  %7.1f cycles per iteration\n", name, lanes, h);
+    }
+}
+
+int main() {
+    double* d;
+    cudaMalloc(&d, 128 * sizeof(double));
+    run<0>("DMUL chain", d);
+    run<1>("DADD chain", d);
+    run<2>("DFMA chain", d);
+    run<3>("DADD + F2F.F32.F64 + F2F.F64.F32", d);
+    run<4>("DADD + integer round-to-f32", d);
+    run<5>("biquad step (DMUL,DADD,DADD,F2F,F2F)", d);
+    run<6>("biquad step with integer rounding", d);
+    run<7>("F2F + FMUL + F2F", d);
+    return 0;
+}
