@@ -89,7 +89,7 @@ int adt_event_elapsed_ms(adt_event* start, adt_event* stop, float* ms); /* syncs
  * EffectFFTFilter.py:143-151 / EffectEQ3BandFFT.py:175-211.
  */
 typedef struct {
-    int32_t fft_size;     /* N: 4096, 8192 or 16384 */
+    int32_t fft_size;     /* N: 4096, 8192, 16384 (or 32768) */
     int32_t hop;          /* 1 <= hop, n0 + hop <= N */
     int32_t n0;           /* 0 <= n0 */
     int32_t back;         /* >= 0 */
@@ -103,6 +103,13 @@ typedef struct {
  * without the 1/N factor.  Copied; the pointer is not retained. */
 int adt_fir_create(adt_ctx* ctx, const adt_fir_desc* desc, const float* mask, adt_fir** out);
 int adt_fir_destroy(adt_fir* fir);
+/* Filters too long for one transform (the reference accepts any chunk size, e.g. Example4.py's 88200) are
+ * PARTITIONED in time: taps = [h_0 | h_1 | ...], y = sum_s (h_s * x) delayed by the segment offset.  Each
+ * segment is an ordinary block plan of its own (its delay folded into `back`); segment 0 stores, the others
+ * accumulate into the same output in segment order.  chunk / n_channels must agree.  Plain float32 I/O only
+ * (no int16 mode, no store epilogue) when n_segments > 1.  adt_fir_create == one segment. */
+int adt_fir_create_segmented(adt_ctx* ctx, int32_t n_segments, const adt_fir_desc* descs, const float* const* masks,
+                             adt_fir** out);
 
 /* Whole-buffer mode on DEVICE buffers (async on the context stream): rows of
  * n_in valid samples in, n_out samples out; equals ceil(n/C) successive

@@ -149,9 +149,10 @@ class SlidingFftEq3:
 # closed form: one causal float64 FIR over the whole stream
 # --------------------------------------------------------------------------
 def stream_delay(chunk: int) -> int:
-    """Delay D such that out[m] = (h * x)[m - D]:
-    D = C - (L-1)/2 = 3C/4 + 1, identical for filters and the EQ composite."""
-    return chunk - (_tap_count(chunk) - 1) // 2
+    """Delay D such that out[m] = (h * x)[m - D] (SURVEY.md Appendix A.4): the slice starts at C + L//2
+    (EffectFFTFilter.py:24,97) of a window whose newest chunk starts at 2C, so D = C - L//2 — for odd L that is
+    C - (L-1)/2 = 3C/4 + 1; identical for filters and the EQ composite, valid for even L too."""
+    return chunk - _tap_count(chunk) // 2
 
 
 def eq3_composite_taps(fs, chunk, f_low, db_low, f_mid, db_mid, f_high, db_high) -> np.ndarray:
@@ -164,7 +165,7 @@ def eq3_composite_taps(fs, chunk, f_low, db_low, f_mid, db_mid, f_high, db_high)
     g_hs, g_ls, g_mid = (10 ** (d / 20) for d in (db_high, db_low, db_mid))
     tot = np.zeros(2 * n - 1)
     tot[:n] += (g_hs - 1) * h_hs + (g_ls - 1) * h_ls
-    tot[(n - 1) // 2] += 1.0
+    tot[n // 2] += 1.0          # the dry middle chunk is exactly C behind: tap index C - D = L//2
     tot += (g_mid - 1) * np.convolve(h_mhp, h_mlp)
     return tot
 

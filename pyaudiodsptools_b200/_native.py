@@ -56,6 +56,7 @@ PROTOTYPES = {
     "adt_event_record": (C.c_int, [_P]),
     "adt_event_elapsed_ms": (C.c_int, [_P, _P, C.POINTER(C.c_float)]),
     "adt_fir_create": (C.c_int, [_P, C.POINTER(FirDesc), _P, C.POINTER(_P)]),
+    "adt_fir_create_segmented": (C.c_int, [_P, C.c_int32, C.POINTER(FirDesc), C.POINTER(_P), C.POINTER(_P)]),
     "adt_fir_destroy": (C.c_int, [_P]),
     "adt_fir_process_dev": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int32]),
     "adt_fir_process_host": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int64, C.c_int32]),

@@ -284,18 +284,27 @@ extern "C" int adt_event_elapsed_ms(adt_event* a, adt_event* b, float* ms) {
 // ---------------------------------------------------------------------------
 // FIR engine
 // ---------------------------------------------------------------------------
-struct adt_fir {
-    adt_ctx* ctx = nullptr;
+// One tap segment of a filter: its own transform size, block geometry, mask and twiddle tables.  Ordinary
+// filters have exactly one; filters too long for one transform are partitioned in time:
+// y = sum_s (h_s * x) delayed by s*Ls, segment 0 stores and segments 1.. accumulate into the same output.
+struct FirSeg {
     adt_fir_desc d{};
     const FirVariant* var = nullptr;
     void* d_mask = nullptr;
     cf* d_coef_x = nullptr;
     cf* d_tw1 = nullptr;
     cf* d_tw2 = nullptr;
+    int resident_ctas = 0;  // CTAs resident at once (SMs x CTAs per SM), computed on first launch
+};
+
+struct adt_fir {
+    adt_ctx* ctx = nullptr;
+    adt_fir_desc d{};          // segment 0 (chunk / n_channels are common to all segments)
+    std::vector<FirSeg> seg;
+    int hist_back = 0;         // max `back` over the segments: samples of history the streaming state keeps
     // streaming state: two [n_channels][hist_pitch] buffers (history ++ newest chunk)
     FirShape shape{0, 0, 0.f, 0.f, 0.f, 0.f};  // store epilogue (adt_fir_set_epilogue)
     unsigned int* d_counter = nullptr;  // work queue heads of the persistent variant, one per stream slot
-    int resident_ctas = 0;  // CTAs resident at once (SMs x CTAs per SM), computed on first launch
     float* d_hist[2] = {nullptr, nullptr};
     int cur = 0;
     int64_t hist_pitch = 0;
@@ -312,27 +321,28 @@ __global__ void fir_set_counter(unsigned int* c, unsigned int v) { *c = v; }
 
 // slot: 0 = the context stream, 1 + i = copy stream i (launches on different streams may overlap, so
 // per-launch device state — the persistent variant's work counter — exists once per slot)
-static int fir_launch(adt_fir* f, cudaStream_t s, const void* x, int64_t in_pitch, int64_t n_in, int64_t in_shift,
-                      void* y, int64_t out_pitch, int64_t n_out, int32_t n_rows, bool i16 = false, int slot = 0) {
+static int fir_launch_seg(adt_fir* f, FirSeg& sg, bool accum, cudaStream_t s, const void* x, int64_t in_pitch,
+                          int64_t n_in, int64_t in_shift, void* y, int64_t out_pitch, int64_t n_out, int32_t n_rows,
+                          bool i16, int slot) {
     adt_ctx* ctx = f->ctx;
     if (n_rows <= 0 || n_out <= 0) return ADT_OK;
-    const int64_t blocks = (n_out + f->d.hop - 1) / f->d.hop;
+    const int64_t blocks = (n_out + sg.d.hop - 1) / sg.d.hop;
     const int64_t pairs = (n_rows + 1) / 2;
     if (blocks > 0x7fffffffLL)
         return adt_set_error(ctx, ADT_ERR_UNSUPPORTED, "too many blocks per row: %lld", (long long)blocks);
     FirKernelArgs a;
     a.x = x;
     a.y = y;
-    a.mask = f->d_mask;
-    a.coef_x = f->d_coef_x;
-    a.tw1 = f->d_tw1;
-    a.tw2 = f->d_tw2;
+    a.mask = sg.d_mask;
+    a.coef_x = sg.d_coef_x;
+    a.tw1 = sg.d_tw1;
+    a.tw2 = sg.d_tw2;
     a.n_rows = n_rows;
     a.blocks_per_row = (int)blocks;
     a.n_items = blocks * pairs;
-    a.g.hop = f->d.hop;
-    a.g.n0 = f->d.n0;
-    a.g.back = f->d.back;
+    a.g.hop = sg.d.hop;
+    a.g.n0 = sg.d.n0;
+    a.g.back = sg.d.back;
     a.g.in_shift = in_shift;
     a.g.n_in = n_in;
     a.g.n_out = n_out;
@@ -344,31 +354,36 @@ static int fir_launch(adt_fir* f, cudaStream_t s, const void* x, int64_t in_pitc
     const bool shaped = f->shape.kind != 0;
     if (shaped && i16)
         return adt_set_error(ctx, ADT_ERR_UNSUPPORTED, "the wave-shaper epilogue is built for float32 I/O only");
-    fir_kernel_fn k = shaped ? (f->d.mask_is_real ? f->var->shaped_real : f->var->shaped_cplx)
-                      : i16  ? (f->d.mask_is_real ? f->var->real_i16 : f->var->cplx_i16)
-                             : (f->d.mask_is_real ? f->var->real : f->var->cplx);
+    if (f->seg.size() > 1 && (shaped || i16))
+        return adt_set_error(ctx, ADT_ERR_UNSUPPORTED, "partitioned (long) filters support plain float32 I/O only");
+    if (accum && !sg.var->accum_real)
+        return adt_set_error(ctx, ADT_ERR_UNSUPPORTED, "kernel family %s has no accumulate variant", sg.var->name);
+    fir_kernel_fn k = shaped ? (sg.d.mask_is_real ? sg.var->shaped_real : sg.var->shaped_cplx)
+                      : i16  ? (sg.d.mask_is_real ? sg.var->real_i16 : sg.var->cplx_i16)
+                             : (sg.d.mask_is_real ? sg.var->real : sg.var->cplx);
     if (a.n_items > 0x7fffffffLL)
         return adt_set_error(ctx, ADT_ERR_UNSUPPORTED, "too many work items: %lld", (long long)a.n_items);
+    if (accum) k = sg.d.mask_is_real ? sg.var->accum_real : sg.var->accum_cplx;
     static const int tma_mode = getenv("ADT_FIR_TMA") ? atoi(getenv("ADT_FIR_TMA")) : 0;   // A/B: TMA-fed window load
-    if (tma_mode && !shaped && !i16 && f->var->tma_real) k = f->d.mask_is_real ? f->var->tma_real : f->var->tma_cplx;
-    if (f->resident_ctas == 0) {  // CTAs in flight at once = how far ahead the L2 prefetch looks
+    if (tma_mode && !shaped && !i16 && !accum && sg.var->tma_real) k = sg.d.mask_is_real ? sg.var->tma_real : sg.var->tma_cplx;
+    if (sg.resident_ctas == 0) {  // CTAs in flight at once = how far ahead the L2 prefetch looks
         int per_sm = 0, sms = 0;
-        CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, f->var->threads, f->var->smem));
+        CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, sg.var->threads, sg.var->smem));
         CK(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
-        f->resident_ctas = per_sm > 0 ? per_sm * sms : sms;
+        sg.resident_ctas = per_sm > 0 ? per_sm * sms : sms;
     }
     // L2 prefetch distance in units of one wave of resident CTAs (measured: flat between 0.25 and 1; 0 = off costs 9 %)
     const double pf = getenv("ADT_FIR_PREFETCH") ? atof(getenv("ADT_FIR_PREFETCH")) : 0.5;
-    a.prefetch_ahead = (int)(pf * f->resident_ctas);
+    a.prefetch_ahead = (int)(pf * sg.resident_ctas);
     unsigned grid = (unsigned)a.n_items;
     // persistent dynamic-queue variant: only worth it when there are several waves of items
     // measured: +1.5 % for the 1-CTA/SM N = 16384 kernel, -5 % for N = 8192 -> default on for 16384 only
-    const int persist_mode = getenv("ADT_FIR_PERSIST") ? atoi(getenv("ADT_FIR_PERSIST")) : (f->d.fft_size == 16384);
-    fir_kernel_fn kp = f->d.mask_is_real ? f->var->persist_real : f->var->persist_cplx;
+    const int persist_mode = getenv("ADT_FIR_PERSIST") ? atoi(getenv("ADT_FIR_PERSIST")) : (sg.d.fft_size == 16384);
+    fir_kernel_fn kp = sg.d.mask_is_real ? sg.var->persist_real : sg.var->persist_cplx;
     bool persistent = false;
-    if (persist_mode && !i16 && !shaped && kp && (persist_mode == 2 || a.n_items >= 4LL * f->resident_ctas)) {   // 2 = force (tests)
+    if (persist_mode && !i16 && !shaped && !accum && kp && (persist_mode == 2 || a.n_items >= 4LL * sg.resident_ctas)) {   // 2 = force (tests)
         if (!f->d_counter) CK(ctx, cudaMalloc((void**)&f->d_counter, (ADT_COPY_STREAMS + 1) * sizeof(unsigned int)));
-        grid = (unsigned)f->resident_ctas;
+        grid = (unsigned)sg.resident_ctas;
         fir_set_counter<<<1, 1, 0, s>>>(f->d_counter + slot, grid);   // first unclaimed item = grid size
         ctx->launches++;
         ex.work_counter = f->d_counter + slot;
@@ -380,34 +395,44 @@ static int fir_launch(adt_fir* f, cudaStream_t s, const void* x, int64_t in_pitc
     ex.blk_skip_from = (int)blocks;
     // split launch: interior blocks by a kernel without any bounds code, edge blocks by the generic one
     static const int split_mode = getenv("ADT_FIR_SPLIT") ? atoi(getenv("ADT_FIR_SPLIT")) : 0;
-    fir_kernel_fn k_int = f->d.mask_is_real ? f->var->split_int_real : f->var->split_int_cplx;
-    fir_kernel_fn k_edge = f->d.mask_is_real ? f->var->split_edge_real : f->var->split_edge_cplx;
-    if (split_mode && !i16 && !shaped && !persistent && k_int) {
-        const int64_t N = f->d.fft_size, hop = f->d.hop, back = f->d.back;
+    fir_kernel_fn k_int = sg.d.mask_is_real ? sg.var->split_int_real : sg.var->split_int_cplx;
+    fir_kernel_fn k_edge = sg.d.mask_is_real ? sg.var->split_edge_real : sg.var->split_edge_cplx;
+    if (split_mode && !i16 && !shaped && !accum && !persistent && k_int) {
+        const int64_t N = sg.d.fft_size, hop = sg.d.hop, back = sg.d.back;
         int64_t b_lo = (back - in_shift + hop - 1) / hop;            // first block with ws >= 0
         if (b_lo < 0) b_lo = 0;
         int64_t b_hi = (n_in - N + back - in_shift) / hop + 1;        // one past the last block with ws + N <= n_in
         if (n_in - N + back - in_shift < 0) b_hi = 0;
         if (b_hi > n_out / hop) b_hi = n_out / hop;                   // ... and a full hop inside the output
         if (b_hi > blocks) b_hi = blocks;
-        if (b_hi - b_lo >= 8 && (b_hi - b_lo) * pairs >= f->resident_ctas) {
+        if (b_hi - b_lo >= 8 && (b_hi - b_lo) * pairs >= sg.resident_ctas) {
             FirExtra ei = ex, ee = ex;
             ei.blk_count = (int)(b_hi - b_lo); ei.blk_offset = (int)b_lo; ei.blk_skip_from = ei.blk_count; ei.blk_skip_len = 0;
             ee.blk_count = (int)(blocks - (b_hi - b_lo)); ee.blk_offset = 0; ee.blk_skip_from = (int)b_lo; ee.blk_skip_len = (int)(b_hi - b_lo);
-            k_int<<<(unsigned)(ei.blk_count * pairs), f->var->threads, f->var->smem, s>>>(a, ei);
+            k_int<<<(unsigned)(ei.blk_count * pairs), sg.var->threads, sg.var->smem, s>>>(a, ei);
             CK(ctx, cudaGetLastError());
             ctx->launches++;
             if (ee.blk_count > 0) {
-                k_edge<<<(unsigned)(ee.blk_count * pairs), f->var->threads, f->var->smem, s>>>(a, ee);
+                k_edge<<<(unsigned)(ee.blk_count * pairs), sg.var->threads, sg.var->smem, s>>>(a, ee);
                 CK(ctx, cudaGetLastError());
                 ctx->launches++;
             }
             return ADT_OK;
         }
     }
-    k<<<grid, f->var->threads, f->var->smem, s>>>(a, ex);
+    k<<<grid, sg.var->threads, sg.var->smem, s>>>(a, ex);
     CK(ctx, cudaGetLastError());
     ctx->launches++;
+    return ADT_OK;
+}
+
+// every tap segment in turn on the same stream: segment 0 stores, the others accumulate
+static int fir_launch(adt_fir* f, cudaStream_t s, const void* x, int64_t in_pitch, int64_t n_in, int64_t in_shift,
+                      void* y, int64_t out_pitch, int64_t n_out, int32_t n_rows, bool i16 = false, int slot = 0) {
+    for (size_t i = 0; i < f->seg.size(); ++i) {
+        int rc = fir_launch_seg(f, f->seg[i], i > 0, s, x, in_pitch, n_in, in_shift, y, out_pitch, n_out, n_rows, i16, slot);
+        if (rc) return rc;
+    }
     return ADT_OK;
 }
 
@@ -415,11 +440,13 @@ extern "C" int adt_fir_destroy(adt_fir* f) {
     if (!f) return ADT_ERR_INVALID;
     cudaSetDevice(f->ctx->device);
     cudaDeviceSynchronize();
-    cudaFree(f->d_mask);
-    cudaFree(f->d_coef_x);
+    for (FirSeg& sg : f->seg) {
+        cudaFree(sg.d_mask);
+        cudaFree(sg.d_coef_x);
+        cudaFree(sg.d_tw1);
+        cudaFree(sg.d_tw2);
+    }
     cudaFree(f->d_counter);
-    cudaFree(f->d_tw1);
-    cudaFree(f->d_tw2);
     cudaFree(f->d_hist[0]);
     cudaFree(f->d_hist[1]);
     cudaFree(f->d_io);
@@ -431,42 +458,62 @@ extern "C" int adt_fir_destroy(adt_fir* f) {
     return ADT_OK;
 }
 
-extern "C" int adt_fir_create(adt_ctx* ctx, const adt_fir_desc* desc, const float* mask, adt_fir** out) {
-    if (!ctx || !desc || !mask || !out) return ADT_ERR_INVALID;
-    *out = nullptr;
+static int fir_build_segment(adt_ctx* ctx, const adt_fir_desc* desc, const float* mask, FirSeg& sg) {
     // Default kernel family (measured): "p32" (32 points/thread) for every size; "p16"
-    // (16 points/thread, 32 warps/SM) is kept as an A/B family.  ADT_FIR_KERNEL overrides.
+    // (16 points/thread, 32 warps/SM) is an A/B family of the AB=1 build.  ADT_FIR_KERNEL overrides.
     const char* want = getenv("ADT_FIR_KERNEL");
     if (!want || !*want) want = "p32";
     const FirVariant* var = find_variant(desc->fft_size, want);
     if (!var)
-        return adt_set_error(ctx, ADT_ERR_UNSUPPORTED, "fft_size %d not in {4096, 8192, 16384}", desc->fft_size);
+        return adt_set_error(ctx, ADT_ERR_UNSUPPORTED, "fft_size %d is not one of the built transform sizes", desc->fft_size);
     if (desc->hop < 1 || desc->n0 < 0 || desc->back < 0 || (int64_t)desc->n0 + desc->hop > desc->fft_size)
         return adt_set_error(ctx, ADT_ERR_INVALID, "bad block geometry: hop=%d n0=%d back=%d N=%d", desc->hop, desc->n0,
                              desc->back, desc->fft_size);
+    sg.d = *desc;
+    sg.var = var;
+    HostTables ht;
+    var->build(mask, desc->mask_is_real != 0, ht);
+    cudaError_t e = cudaMalloc(&sg.d_mask, ht.coef_s.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&sg.d_tw1, ht.tw1.size() * sizeof(cf));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&sg.d_tw2, ht.tw2.size() * sizeof(cf));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&sg.d_coef_x, ht.coef_x.size() * sizeof(float) + 8);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(sg.d_mask, ht.coef_s.data(), ht.coef_s.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !ht.coef_x.empty())
+        e = cudaMemcpy(sg.d_coef_x, ht.coef_x.data(), ht.coef_x.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(sg.d_tw1, ht.tw1.data(), ht.tw1.size() * sizeof(cf), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(sg.d_tw2, ht.tw2.data(), ht.tw2.size() * sizeof(cf), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return adt_cuda_fail(ctx, e, "adt_fir_create (tables)");
+    return ADT_OK;
+}
+
+extern "C" int adt_fir_create_segmented(adt_ctx* ctx, int32_t n_segments, const adt_fir_desc* descs,
+                                        const float* const* masks, adt_fir** out) {
+    if (!ctx || !descs || !masks || !out || n_segments < 1 || n_segments > 64) return ADT_ERR_INVALID;
+    *out = nullptr;
+    const adt_fir_desc* desc = &descs[0];
     if (desc->chunk < 0 || desc->n_channels < 0 || ((desc->chunk > 0) != (desc->n_channels > 0)))
         return adt_set_error(ctx, ADT_ERR_INVALID, "chunk and n_channels must both be > 0 or both be 0");
+    for (int i = 0; i < n_segments; ++i)
+        if (!masks[i] || descs[i].chunk != desc->chunk || descs[i].n_channels != desc->n_channels)
+            return adt_set_error(ctx, ADT_ERR_INVALID, "segment %d: null mask or chunk / n_channels differ from segment 0", i);
     CK(ctx, cudaSetDevice(ctx->device));
     adt_fir* f = new (std::nothrow) adt_fir();
     if (!f) return ADT_ERR_NOMEM;
     f->ctx = ctx;
     f->d = *desc;
-    f->var = var;
-    HostTables ht;
-    var->build(mask, desc->mask_is_real != 0, ht);
-    const std::vector<cf>&tw1 = ht.tw1, &tw2 = ht.tw2;
-    cudaError_t e = cudaMalloc(&f->d_mask, ht.coef_s.size() * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_tw1, tw1.size() * sizeof(cf));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_tw2, tw2.size() * sizeof(cf));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&f->d_coef_x, ht.coef_x.size() * sizeof(float) + 8);
-    if (e == cudaSuccess)
-        e = cudaMemcpy(f->d_mask, ht.coef_s.data(), ht.coef_s.size() * sizeof(float), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && !ht.coef_x.empty())
-        e = cudaMemcpy(f->d_coef_x, ht.coef_x.data(), ht.coef_x.size() * sizeof(float), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(f->d_tw1, tw1.data(), tw1.size() * sizeof(cf), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(f->d_tw2, tw2.data(), tw2.size() * sizeof(cf), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && desc->n_channels > 0) {
-        f->hist_pitch = ((int64_t)desc->back + desc->chunk + 31) / 32 * 32;
+    f->seg.resize((size_t)n_segments);
+    for (int i = 0; i < n_segments; ++i) {
+        int rc = fir_build_segment(ctx, &descs[i], masks[i], f->seg[(size_t)i]);
+        if (rc) {
+            adt_fir_destroy(f);
+            return rc;
+        }
+        if (descs[i].back > f->hist_back) f->hist_back = descs[i].back;
+    }
+    cudaError_t e = cudaSuccess;
+    if (desc->n_channels > 0) {
+        f->hist_pitch = ((int64_t)f->hist_back + desc->chunk + 31) / 32 * 32;
         const size_t hb = (size_t)desc->n_channels * f->hist_pitch * sizeof(float);
         for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
             e = cudaMalloc((void**)&f->d_hist[i], hb);
@@ -480,6 +527,11 @@ extern "C" int adt_fir_create(adt_ctx* ctx, const adt_fir_desc* desc, const floa
     }
     *out = f;
     return ADT_OK;
+}
+
+extern "C" int adt_fir_create(adt_ctx* ctx, const adt_fir_desc* desc, const float* mask, adt_fir** out) {
+    if (!ctx || !desc || !mask || !out) return ADT_ERR_INVALID;
+    return adt_fir_create_segmented(ctx, 1, desc, &mask, out);
 }
 
 // Attach (kind 1 saturator / 2 soft clipper) or detach (kind 0) a wave-shaper applied to every output
@@ -600,12 +652,13 @@ extern "C" int adt_fir_process_host_i16(adt_fir* f, const int16_t* x, int64_t in
 // One streaming step on device buffers: hist[cur] = [last `back` samples | new chunk].
 static int fir_apply_common(adt_fir* f, const float* in, cudaMemcpyKind in_kind, float* out_dev) {
     adt_ctx* ctx = f->ctx;
-    const int C = f->d.chunk, rows = f->d.n_channels, back = f->d.back;
+    const int C = f->d.chunk, rows = f->d.n_channels, back = f->hist_back;
     float* cur = f->d_hist[f->cur];
     float* nxt = f->d_hist[f->cur ^ 1];
     cudaStream_t s = ctx->stream;
     CK(ctx, cudaMemcpy2DAsync(cur + back, f->hist_pitch * sizeof(float), in, (size_t)C * sizeof(float),
                               (size_t)C * sizeof(float), rows, in_kind, s));
+    // the chunk starts at buffer offset `back`; a segment's window for block b starts `its own back` before b*hop
     int rc = fir_launch(f, s, cur, f->hist_pitch, (int64_t)back + C, back, out_dev, C, C, rows);
     if (rc) return rc;
     if (back > 0)

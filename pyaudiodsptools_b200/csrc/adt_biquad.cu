@@ -193,18 +193,27 @@ __global__ void __launch_bounds__(96) biquad3_kernel(const T* __restrict__ x, T*
             for (int i = 0; i < 32; ++i) nxt[i] = (i < rows && nb + lane < n) ? xr[(long long)i * pitch + nb] : T(0);
         }
         if (active && live) {
-            for (int j = 0; j < w; ++j) {
+            // Full tiles run a fixed 32-iteration loop, unrolled so that the loads, the float -> double
+            // conversions and the feed-forward sum of later samples are issued while the feedback chain
+            // (DMUL -> DSUB -> DSUB -> round) of earlier ones is still in flight.
+            auto one = [&](int j) {
                 const double xin = (double)src[lane][j];
-                double acc = __dmul_rn(k.c[0], x1);
-                acc = __dadd_rn(acc, __dmul_rn(k.c[1], x2));
-                acc = __dadd_rn(acc, __dmul_rn(k.c[2], x3));
-                acc = __dsub_rn(acc, __dmul_rn(k.c[3], y1));
+                double ff = __dmul_rn(k.c[0], x1);
+                ff = __dadd_rn(ff, __dmul_rn(k.c[1], x2));
+                ff = __dadd_rn(ff, __dmul_rn(k.c[2], x3));
+                double acc = __dsub_rn(ff, __dmul_rn(k.c[3], y1));
                 acc = __dsub_rn(acc, __dmul_rn(k.c[4], y2));
                 T out;
                 const double fb = BiquadRound<T, ROUND_INT>::run(acc, &out);
                 dst[lane][j] = out;
                 x3 = x2; x2 = x1; x1 = xin;
                 y2 = y1; y1 = fb;
+            };
+            if (w == 32) {
+#pragma unroll 8
+                for (int j = 0; j < 32; ++j) one(j);
+            } else {
+                for (int j = 0; j < w; ++j) one(j);
             }
         }
         if (band == 2 && active) {

@@ -530,7 +530,7 @@ ADT_HD float fir_shape(const FirShape& sh, float v);
 // z[n], n = n1*M1 + t + u*T, goes to y[m0 + n - n0] when 0 <= n - n0 < hop and
 // the stream index is below n_out.  `lim` = min(hop, n_out - m0) folds both
 // upper bounds into one unsigned compare per element.
-template <class C, class IO, bool SHAPED>
+template <class C, class IO, bool SHAPED, bool ACCUM = false>
 ADT_HD void store_slice_impl(const cf* v, int t, typename IO::elem* __restrict__ ya, typename IO::elem* __restrict__ yb,
                              long long m0, const FirGeom& g, const FirShape& shape) {
     const long long room = g.n_out - m0;
@@ -544,17 +544,22 @@ ADT_HD void store_slice_impl(const cf* v, int t, typename IO::elem* __restrict__
             constexpr int off = n1 * C::M1 + u * C::T;
             const cf z = v[u * C::N1 + brev<C::N1>(n1)];
             const bool ok = (unsigned)(jt + off) < lim;
-            if (ok) IO::store(pa + off, (SHAPED ? fir_shape(shape, z.x) : z.x));
-            if (ok && pb) IO::store(pb + off, (SHAPED ? fir_shape(shape, z.y) : z.y));
+            if constexpr (ACCUM) {   // later tap segments of a partitioned filter add to what is already there
+                if (ok) pa[off] += z.x;
+                if (ok && pb) pb[off] += z.y;
+            } else {
+                if (ok) IO::store(pa + off, (SHAPED ? fir_shape(shape, z.x) : z.x));
+                if (ok && pb) IO::store(pb + off, (SHAPED ? fir_shape(shape, z.y) : z.y));
+            }
         });
     });
 }
 
 // SHAPED kernels are separate instantiations, so the default kernels carry no epilogue code at all.
-template <class C, class IO = IoF32, bool SHAPED = false>
+template <class C, class IO = IoF32, bool SHAPED = false, bool ACCUM = false>
 ADT_HD void store_slice(const cf* v, int t, typename IO::elem* __restrict__ ya, typename IO::elem* __restrict__ yb,
                         long long m0, const FirGeom& g, const FirShape& shape) {
-    store_slice_impl<C, IO, SHAPED>(v, t, ya, yb, m0, g, shape);
+    store_slice_impl<C, IO, SHAPED, ACCUM>(v, t, ya, yb, m0, g, shape);
 }
 
 }  // namespace adt

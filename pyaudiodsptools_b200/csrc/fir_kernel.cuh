@@ -96,7 +96,7 @@ __device__ __forceinline__ void fir_prefetch_l2(const FirKernelArgs& a, long lon
 
 // One CTA per work item (the default).  Persistent CTA loops were measured slower at N = 8192 on B200
 // (static stride -15 %, dynamic queue -5 %); see fir_persist_kernel below and DESIGN.md §5.4.
-template <class C, class MaskT, int MIN_CTAS, class IO = IoF32, bool SHAPED = false>
+template <class C, class MaskT, int MIN_CTAS, class IO = IoF32, bool SHAPED = false, bool ACCUM = false>
 __global__ void __launch_bounds__(C::T, MIN_CTAS) fir_block_kernel(const FirKernelArgs a, const FirExtra ex) {
     typedef typename IO::elem E;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(C::T, MIN_CTAS) fir_block_kernel(const FirKern
     inv_stage2<C>(v, t, a.tw2, tile);
     __syncthreads();
     inv_stage1<C>(v, t, a.tw1, tile);
-    store_slice<C, IO, SHAPED>(v, t, it.ya, it.yb, it.m0, a.g, ex.shape);
+    store_slice<C, IO, SHAPED, ACCUM>(v, t, it.ya, it.yb, it.m0, a.g, ex.shape);
 }
 
 // TMA-FED variant (A/B, ADT_FIR_TMA=1): the two row windows of an interior item are brought

@@ -33,6 +33,7 @@ struct FirVariant {
     fir_kernel_fn shaped_cplx, shaped_real;    // float32 I/O with the wave-shaper store epilogue
     fir_kernel_fn split_int_cplx, split_int_real, split_edge_cplx, split_edge_real;  // split launch (p32) or null
     fir_kernel_fn tma_cplx, tma_real;          // TMA-fed window load (A/B, ADT_FIR_TMA=1) or null
+    fir_kernel_fn accum_cplx, accum_real;      // y += result: tap segments 1.. of a partitioned (long) filter, or null
     void (*build)(const float* mask, bool real_only, HostTables& out);
 };
 
@@ -57,6 +58,8 @@ FirVariant make_variant32(const char* name) {
     v.shaped_cplx = fir_block_kernel<C, cf, MIN_CTAS, IoF32, true>;
     v.shaped_real = fir_block_kernel<C, float, MIN_CTAS, IoF32, true>;
     v.split_int_cplx = v.split_int_real = v.split_edge_cplx = v.split_edge_real = nullptr;
+    v.accum_cplx = fir_block_kernel<C, cf, MIN_CTAS, IoF32, false, true>;
+    v.accum_real = fir_block_kernel<C, float, MIN_CTAS, IoF32, false, true>;
     v.tma_cplx = v.tma_real = nullptr;
     if constexpr (TMA) {
         v.tma_cplx = fir_tma_kernel<C, cf, MIN_CTAS>;
@@ -93,6 +96,7 @@ FirVariant make_variant16(const char* name) {
     v.shaped_real = fir16_block_kernel<C, float, MIN_CTAS, IoF32, true>;
     v.split_int_cplx = v.split_int_real = v.split_edge_cplx = v.split_edge_real = nullptr;
     v.tma_cplx = v.tma_real = nullptr;
+    v.accum_cplx = v.accum_real = nullptr;
     v.build = [](const float* mask, bool real_only, HostTables& out) {
         out.tw1 = build16_tw1<C>();
         out.tw2 = build16_tw2<C>();

@@ -17,16 +17,17 @@ import numpy as np
 
 SUPPORTED_FFT = (4096, 8192, 16384)
 
-
 def filter_length(chunk: int) -> int:
     return chunk // 2 - 1  # EffectFFTFilter.py:22
 
 
 def stream_delay(chunk: int) -> int:
     """D with out[m] = sum_k h[k] x[m - D - k]: the reference slices the
-    3-chunk window at C + L//2 (EffectFFTFilter.py:24), i.e. zero-phase on the
-    previous chunk -> D = C - (L-1)/2."""
-    return chunk - (filter_length(chunk) - 1) // 2
+    3-chunk window at C + L//2 (EffectFFTFilter.py:24,97), so the sample that
+    meets h[0] is 2C - (C + L//2) = C - L//2 behind the output index — for the
+    usual odd L that is zero-phase on the previous chunk, D = C - (L-1)/2; the
+    same formula covers chunk sizes that give an even L (e.g. 882, 441)."""
+    return chunk - filter_length(chunk) // 2
 
 
 def _lowpass(cut_hz, fs, n, window):
@@ -63,7 +64,7 @@ def eq3_taps(fs, chunk, f_low, db_low, f_mid, db_mid, f_high, db_high):
     g_hs, g_ls, g_mid = (10.0 ** (db / 20.0) for db in (db_high, db_low, db_mid))  # :195,:200,:205
     h = (g_mid - 1.0) * mid
     h[:n] += (g_hs - 1.0) * hs + (g_ls - 1.0) * ls
-    h[(n - 1) // 2] += 1.0  # the dry middle chunk, :209
+    h[n // 2] += 1.0  # the dry middle chunk (:209) sits exactly C behind: tap index C - D = L//2
     return h
 
 
@@ -81,26 +82,47 @@ class BlockPlan:
 
 # Measured cost of one FFT point (kernel time per transform point, relative to N = 8192) on B200,
 # gpurun_out/q7: the 4-CTA/SM N = 4096 kernels overlap memory and FP phases best, the 1-CTA/SM
-# N = 16384 kernel worst.  The planner minimises cost / (hop / N).
+# N = 16384 kernel worst.  The planner minimises  segments * cost * N / hop.
 _POINT_COST = {4096: 0.82, 8192: 1.00, 16384: 1.36}
+_ALIGN_SLACK = 64          # worst-case loss of hop to the 32-sample alignment of n0 and hop (plan_block)
+_MAX_SEGMENTS = 64
 
 
-def _pick_fft_size(n_taps: int) -> int:
-    forced = os.environ.get("ADT_FFT_SIZE")
-    if forced:
-        return int(forced)
+def _plan_sizes(n_taps: int, fft_size: int | None = None):
+    """(fft_size, n_segments, taps_per_segment) with the lowest estimated cost per output sample.
+
+    One segment whenever the filter fits a transform with a useful hop; otherwise the taps are partitioned
+    in time into equal segments (each its own overlap-save pass, the later ones accumulating — DESIGN.md
+    §3.1), which is what makes every chunk size the reference accepts work here too."""
+    forced = fft_size or (int(os.environ["ADT_FFT_SIZE"]) if os.environ.get("ADT_FFT_SIZE") else None)
+    if forced and forced not in SUPPORTED_FFT:
+        raise ValueError(f"fft_size {forced} not in {SUPPORTED_FFT}")
     best = None
     for n, cost in _POINT_COST.items():
-        hop = n - (n_taps - 1) - 32        # 32: worst-case alignment slack of plan_block
-        if hop < 32:
+        if n not in SUPPORTED_FFT or (forced and n != forced):
             continue
-        score = cost * n / hop
-        if best is None or score < best[0]:
-            best = (score, n)
+        for segs in range(1, _MAX_SEGMENTS + 1):
+            per = -(-n_taps // segs)
+            hop = n - (per - 1) - _ALIGN_SLACK
+            if hop < 32:
+                continue
+            score = segs * cost * n / hop
+            if best is None or score < best[0] - 1e-12:
+                best = (score, n, segs, per)
+            if hop >= n // 2:
+                break              # more segments only add passes from here on
     if best is None:
-        raise ValueError(f"a {n_taps}-tap filter needs an FFT larger than {SUPPORTED_FFT[-1]} "
-                         "(chunk_size too large for this build)")
-    return best[1]
+        raise ValueError(f"a {n_taps}-tap filter cannot be planned with FFT sizes {SUPPORTED_FFT}")
+    return best[1], best[2], best[3]
+
+
+def plan_filter(taps: np.ndarray, delay: int, fft_size: int | None = None):
+    """List of BlockPlans (one per tap segment) for  y[m] = sum_k taps[k] x[m - delay - k]."""
+    taps = np.asarray(taps, dtype=np.float64)
+    n, segs, per = _plan_sizes(len(taps), fft_size)
+    if segs == 1:
+        return [plan_block(taps, delay, n)]
+    return [plan_block(taps[i:i + per], delay + i, n) for i in range(0, len(taps), per)]
 
 
 def plan_block(taps: np.ndarray, delay: int, fft_size: int | None = None) -> BlockPlan:
@@ -113,7 +135,7 @@ def plan_block(taps: np.ndarray, delay: int, fft_size: int | None = None) -> Blo
     back = delay + c + n0."""
     taps = np.asarray(taps, dtype=np.float64)
     t = len(taps)
-    n = fft_size or _pick_fft_size(t)
+    n = fft_size or _plan_sizes(t)[0]
     if n not in SUPPORTED_FFT:
         raise ValueError(f"fft_size {n} not in {SUPPORTED_FFT}")
     c = (t - 1) // 2

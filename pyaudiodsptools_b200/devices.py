@@ -33,9 +33,22 @@ def _snapshot_config():
     if fs is None or chunk is None:
         raise TypeError("config.initialize(sampling_rate, chunk_size) must be called before creating devices")
     chunk = int(chunk)
-    if chunk < 8 or chunk % 4:
-        raise ValueError("chunk_size must be a multiple of 4 (the reference needs an odd filter length C//2 - 1)")
+    if chunk < 8:
+        raise ValueError("chunk_size must be at least 8 (the filter has chunk_size // 2 - 1 taps)")
     return fs, chunk
+
+
+def _check_out(out, shape, dtype, flat_ok=False):
+    """The C library writes through the raw pointer: a wrong-sized or wrong-typed ``out=`` must never reach it
+    (explicit checks, not asserts — they survive ``python -O``)."""
+    if not isinstance(out, np.ndarray):
+        raise TypeError("out must be a numpy array")
+    if out.dtype != dtype:
+        raise TypeError(f"out must have dtype {np.dtype(dtype).name}, got {out.dtype}")
+    if not out.flags["C_CONTIGUOUS"] or not out.flags["WRITEABLE"]:
+        raise ValueError("out must be C-contiguous and writeable")
+    if (out.size != int(np.prod(shape))) if flat_ok else (out.shape != tuple(shape)):
+        raise ValueError(f"out must have shape {tuple(shape)}, got {out.shape}")
 
 
 class _FirDevice:
@@ -47,14 +60,22 @@ class _FirDevice:
         self.chunk_size = chunk
         self.channels = int(channels)
         self.taps = taps
-        self.plan = design.plan_block(taps, design.stream_delay(chunk), fft_size)
+        # one block plan per tap segment: a single one unless the filter is too long for one transform
+        self.plans = design.plan_filter(taps, design.stream_delay(chunk), fft_size)
+        self.plan = self.plans[0]
+        self.n_segments = len(self.plans)
         self._ctx = _native.default_context(device)
-        desc = _native.FirDesc(self.plan.fft_size, self.plan.hop, self.plan.n0, self.plan.back,
-                               int(self.plan.mask_is_real), chunk, self.channels, 0)
-        mask = np.ascontiguousarray(self.plan.mask).view(np.float32)
+        descs = (_native.FirDesc * self.n_segments)(*[
+            _native.FirDesc(p.fft_size, p.hop, p.n0, p.back, int(p.mask_is_real), chunk, self.channels, 0)
+            for p in self.plans])
+        masks = [np.ascontiguousarray(p.mask).view(np.float32) for p in self.plans]
+        mask_ptrs = (C.c_void_p * self.n_segments)(*[m.ctypes.data for m in masks])
         h = C.c_void_p()
-        self._ctx.check(self._ctx.lib.adt_fir_create(self._ctx.h, C.byref(desc), mask.ctypes.data, C.byref(h)))
+        self._ctx.check(self._ctx.lib.adt_fir_create_segmented(self._ctx.h, self.n_segments, descs, mask_ptrs,
+                                                               C.byref(h)))
         self._h = h
+        if epilogue is not None and self.n_segments > 1:
+            raise ValueError("a store epilogue cannot be fused into a partitioned (long) filter")
         self.set_epilogue(epilogue)
 
     def set_epilogue(self, shaper=None):
@@ -80,7 +101,7 @@ class _FirDevice:
         if out is None:
             y = np.empty(self.channels * self.chunk_size, dtype=np.float32)
         else:
-            assert out.dtype == np.float32 and out.size == flat.size and out.flags["C_CONTIGUOUS"]
+            _check_out(out, (flat.size,), np.float32, flat_ok=True)
             y = out.reshape(-1)
         self._ctx.check(self._ctx.lib.adt_fir_apply_host(self._h, x.ctypes.data, y.ctypes.data))
         return y if self.channels == 1 else y.reshape(self.channels, self.chunk_size)
@@ -100,7 +121,7 @@ class _FirDevice:
         n_out = self.out_length(n)
         if out is None:
             out = np.empty((rows, n_out), dtype=np.float32)
-        assert out.shape == (rows, n_out) and out.dtype == np.float32 and out.flags["C_CONTIGUOUS"]
+        _check_out(out, (rows, n_out), np.float32)
         self._ctx.check(self._ctx.lib.adt_fir_process_host(self._h, x2.ctypes.data, n, n, out.ctypes.data, n_out,
                                                            n_out, rows))
         return out[0] if one_d else out
@@ -118,7 +139,7 @@ class _FirDevice:
         n_out = self.out_length(n)
         if out is None:
             out = np.empty((rows, n_out), dtype=np.int16)
-        assert out.shape == (rows, n_out) and out.dtype == np.int16 and out.flags["C_CONTIGUOUS"]
+        _check_out(out, (rows, n_out), np.int16)
         self._ctx.check(self._ctx.lib.adt_fir_process_host_i16(self._h, x2.ctypes.data, n, n, out.ctypes.data, n_out,
                                                                n_out, rows))
         return out[0] if one_d else out

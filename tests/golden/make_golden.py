@@ -49,7 +49,11 @@ def main():
     ref = _import_reference()
     numpy_version = np.__version__
 
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]     # optional name prefixes: regenerate a subset
+
     def fft_case(name, fs, chunk, kind, args, x):
+        if only and not any(name.startswith(o) for o in only):
+            return
         ref.config.initialize(fs, chunk)
         ctor = {"lowcut": ref.CreateLowCutFilter, "highcut": ref.CreateHighCutFilter,
                 "eq3fft": ref.CreateEQ3BandFFT}[kind]
@@ -78,6 +82,14 @@ def main():
     # --- config 4: high-cut 4 kHz chunk sweep ----------------------------------------
     for c, nch in ((512, 12), (1024, 8), (4096, 5), (16384, 4)):
         fft_case(f"highcut4000_c{c}_noise", 44100, c, "highcut", (4000,), _noise(4000 + c, nch * c))
+    # --- round 2: chunk sizes beyond one transform and chunk sizes that are not multiples of 4 ---------
+    # EQ at C = 16384 (16381-tap composite), Example4.py's chunk 88200 (44099 taps -> partitioned filter),
+    # C = 882 / 441 (even / odd filter length: the reference runs them, EffectFFTFilter.py:22-25)
+    fft_case("eq3fft_c16384_noise", 44100, 16384, "eq3fft", (100, 2, 700, -4, 8000, 5), _noise(16384, 4 * 16384))
+    fft_case("lowcut800_c88200_noise", 44100, 88200, "lowcut", (800,), _noise(88200, 3 * 88200))
+    fft_case("lowcut300_c882_noise", 44100, 882, "lowcut", (300,), _noise(882, 7 * 882))
+    fft_case("eq3fft_c882_noise", 44100, 882, "eq3fft", (100, 2, 700, -4, 8000, 5), _noise(883, 7 * 882))
+    fft_case("highcut4000_c441_noise", 44100, 441, "highcut", (4000,), _noise(441, 9 * 441))
     # --- config 5: 96 kHz low-cut ----------------------------------------------------
     fft_case("lowcut800_c4096_96k_noise", 96000, 4096, "lowcut", (800,), _noise(96, 5 * 4096))
     # --- defaults and edge inputs ----------------------------------------------------
@@ -89,6 +101,8 @@ def main():
     fft_case("eq3fft_c512_square", 44100, 512, "eq3fft", (250, -6, 1200, 3, 6000, -2), sq)
     fft_case("highcut4000_c512_zeros", 44100, 512, "highcut", (4000,), np.zeros(4 * 512, dtype="float32"))
 
+    if only:
+        return
     # --- the streaming biquad (EffectEQ3Band.py:90-180) -------------------------------
     for tag, dtype in (("f32", "float32"), ("f64", "float64")):
         eq = ref.CreateEQ3Band(100, 2, 700, -4, 8000, 5)

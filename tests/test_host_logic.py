@@ -40,13 +40,17 @@ def _overlap_save_numpy(plan, x, n_out):
 
 @pytest.mark.parametrize("name", golden_fft_cases())
 def test_block_plan_reproduces_reference(name):
+    """Every golden vector of the reference is reproduced by the block plan(s) replayed in float64 numpy —
+    one plan for ordinary filters, several accumulated tap segments for the long ones (EQ at C = 16384,
+    Example4.py's chunk 88200), including chunk sizes that give an even filter length (882) or are odd (441)."""
     meta, arr = load_golden(name)
-    if meta["chunk"] > 8192 and meta["kind"] == "eq3fft":
-        pytest.skip("needs an FFT larger than this build supports")
-    plan = design.plan_block(_taps_for(meta), design.stream_delay(meta["chunk"]))
-    assert plan.n0 % 32 == 0 and plan.hop % 32 == 0 and plan.back % 32 == 0
-    assert plan.n0 + plan.hop <= plan.fft_size
-    y = _overlap_save_numpy(plan, arr["x"].astype(np.float64), len(arr["y"]))
+    plans = design.plan_filter(_taps_for(meta), design.stream_delay(meta["chunk"]))
+    y = np.zeros(len(arr["y"]))
+    for plan in plans:
+        assert plan.n0 % 32 == 0 and plan.hop % 32 == 0
+        assert plan.back % 32 == 0 or (plan.mask_is_real and meta["chunk"] % 4)   # unaligned windows only for odd chunk sizes
+        assert plan.n0 + plan.hop <= plan.fft_size
+        y += _overlap_save_numpy(plan, arr["x"].astype(np.float64), len(arr["y"]))
     assert rms(y - arr["y"]) <= 1e-7          # complex64 mask rounding + the reference's own noise
     assert np.max(np.abs(y - arr["y"])) <= 2e-6
 
@@ -70,9 +74,15 @@ def test_design_equals_oracle_design():
         assert design.stream_delay(c) == oracle.stream_delay(c) == 3 * c // 4 + 1
 
 
-def test_eq_too_large_is_rejected():
+def test_long_filters_are_partitioned():
+    """A filter that does not fit one transform is split into equal tap segments whose delays tile the taps."""
     with pytest.raises(ValueError):
-        design.plan_block(np.ones(16381), design.stream_delay(16384))
+        design.plan_block(np.ones(40000), design.stream_delay(16384))        # one block plan cannot hold it ...
+    taps = np.random.default_rng(0).standard_normal(44099)
+    plans = design.plan_filter(taps, 100)                                     # ... the segmented planner can
+    assert len(plans) > 1 and sum(p.n_taps for p in plans) == len(taps)
+    assert [p.delay for p in plans] == list(np.cumsum([100] + [p.n_taps for p in plans[:-1]]))
+    assert len(design.plan_filter(taps[:2047], 3073)) == 1
 
 
 def test_biquad_coefficients_match_oracle():
@@ -172,3 +182,28 @@ def test_block_plan_random_filters(seed):
     got = _overlap_save_numpy(plan, x, n)
     scale = np.sqrt(np.mean(want ** 2)) + 1e-30
     assert rms(got - want) / scale < 2e-6       # complex64 mask rounding only
+
+
+def test_wav_helpers_round_trip(tmp_path):
+    """The file boundary of Example1/2.py (Utility.py:218-312): int16/32768 on load, int16(x*32767) on store,
+    [2, n] transposed to frames; plus the aliases that make the reference's scripts run after an import swap."""
+    import pyaudiodsptools_b200 as adt
+    adt.config.initialize(22050, 512)
+    rng = np.random.default_rng(0)
+    mono = rng.uniform(-1, 1, 1000).astype(np.float32)
+    p = str(tmp_path / "m.wav")
+    adt.NumpyFloatToWav(p, mono)
+    back = adt.Utility.MonoWavToNumpyFloat(p)
+    assert back.dtype == np.float32
+    assert np.array_equal(back, (mono * 32767).astype(np.int16).astype(np.float32) / 32768)
+    assert np.array_equal(adt.MonoWavToNumpy16BitInt(p), (mono * 32767).astype(np.int16))
+    st = rng.uniform(-1, 1, (2, 700)).astype(np.float32)
+    q = str(tmp_path / "s.wav")
+    adt.NumpyFloatToWav(q, st)
+    left, right = adt.Utility.StereoWavToNumpyFloat(q)
+    assert np.array_equal(left, (st[0] * 32767).astype(np.int16).astype(np.float32) / 32768)
+    assert np.array_equal(right, (st[1] * 32767).astype(np.int16).astype(np.float32) / 32768)
+    with pytest.raises(ValueError):
+        adt.Utility.StereoWavToNumpyFloat(p)
+    assert np.array_equal(adt.MixSignals(mono, mono), np.clip(mono.astype(np.float64) * 2, -1, 1))
+    assert adt.CreateLowCutFilterGPU is adt.CreateLowCutFilter and adt.CreateEQ3BandFFTGPU is adt.CreateEQ3BandFFT
