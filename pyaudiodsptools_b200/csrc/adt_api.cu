@@ -76,6 +76,8 @@ const FirVariant* const* all_variants(int* count) {
         fir_variant_p32_4096(),   // N = 4096,  128 threads, 4 CTAs/SM
         fir_variant_p32_8192(),   // N = 8192,  256 threads, 2 CTAs/SM  (headline kernel)
         fir_variant_p32_16384(),  // N = 16384, 512 threads, 1 CTA/SM
+        fir_variant_c4_32768(),   // N = 32768, 4-CTA cluster x 256 threads, DSMEM exchange
+        fir_variant_c2_16384(),   // N = 16384, 2-CTA cluster (ADT_FIR_KERNEL=c2)
         fir_variant_p16_4096(),   // A/B family, null unless built with AB=1
         fir_variant_p16_8192(),
     };
@@ -129,7 +131,8 @@ extern "C" int adt_ctx_create(int device, adt_ctx** out) {
         if (!v) continue;
         for (fir_kernel_fn f : {v->cplx, v->real, v->cplx_i16, v->real_i16, v->persist_cplx, v->persist_real,
                                 v->shaped_cplx, v->shaped_real, v->split_int_cplx, v->split_int_real,
-                                v->split_edge_cplx, v->split_edge_real, v->tma_cplx, v->tma_real}) {
+                                v->split_edge_cplx, v->split_edge_real, v->tma_cplx, v->tma_real, v->accum_cplx,
+                                v->accum_real}) {
             if (!f) continue;
             e = cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->smem);
             if (e == cudaSuccess && getenv("ADT_FIR_CARVEOUT"))  // tuning knob: % of the 228 KB given to shared memory
@@ -364,6 +367,9 @@ static int fir_launch_seg(adt_fir* f, FirSeg& sg, bool accum, cudaStream_t s, co
     if (a.n_items > 0x7fffffffLL)
         return adt_set_error(ctx, ADT_ERR_UNSUPPORTED, "too many work items: %lld", (long long)a.n_items);
     if (accum) k = sg.d.mask_is_real ? sg.var->accum_real : sg.var->accum_cplx;
+    if (!k)
+        return adt_set_error(ctx, ADT_ERR_UNSUPPORTED, "kernel family %s (N = %d) has no %s variant", sg.var->name, sg.var->n,
+                             shaped ? "store-epilogue" : i16 ? "int16" : "such");
     static const int tma_mode = getenv("ADT_FIR_TMA") ? atoi(getenv("ADT_FIR_TMA")) : 0;   // A/B: TMA-fed window load
     if (tma_mode && !shaped && !i16 && !accum && sg.var->tma_real) k = sg.d.mask_is_real ? sg.var->tma_real : sg.var->tma_cplx;
     if (sg.resident_ctas == 0) {  // CTAs in flight at once = how far ahead the L2 prefetch looks
@@ -419,6 +425,24 @@ static int fir_launch_seg(adt_fir* f, FirSeg& sg, bool accum, cudaStream_t s, co
             }
             return ADT_OK;
         }
+    }
+    if (sg.var->cluster > 1) {   // one thread-block cluster per work item
+        if (a.n_items * sg.var->cluster > 0x7fffffffLL)
+            return adt_set_error(ctx, ADT_ERR_UNSUPPORTED, "too many work items: %lld", (long long)a.n_items);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(a.n_items * sg.var->cluster));
+        cfg.blockDim = dim3((unsigned)sg.var->threads);
+        cfg.dynamicSmemBytes = sg.var->smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)sg.var->cluster;
+        attr[0].val.clusterDim.y = attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CK(ctx, cudaLaunchKernelEx(&cfg, k, a, ex));
+        ctx->launches++;
+        return ADT_OK;
     }
     k<<<grid, sg.var->threads, sg.var->smem, s>>>(a, ex);
     CK(ctx, cudaGetLastError());

@@ -61,6 +61,30 @@ inline std::vector<float> permute_mask(const float* mask_natural, bool real_only
     return out;
 }
 
+// Cluster transform (fir_cluster.cuh): CTA `rank` owns the sub-transforms k1 in [rank*K1L, (rank+1)*K1L); its
+// slice of the mask is stored at [(rank*32 + k3)*T + t] for the bin  k1 + N1*k2 + N1*N2*k3  that thread t holds in
+// register k3 after forward stage 3.
+template <class C>
+inline std::vector<float> permute_mask_cluster(const float* mask_natural, bool real_only) {
+    const double inv = 1.0 / (double)C::N;
+    std::vector<float> out((size_t)C::N * (real_only ? 1 : 2));
+    for (int rank = 0; rank < C::CS; ++rank)
+        for (int k3 = 0; k3 < 32; ++k3)
+            for (int t = 0; t < C::T; ++t) {
+                const int row = C::stage3_row(t);
+                const int k1 = rank * C::K1L + row / C::N2, k2 = row % C::N2;
+                const int k = k1 + C::N1 * k2 + C::N1 * C::N2 * k3;
+                const size_t o = ((size_t)rank * 32 + k3) * C::T + t;
+                if (real_only) {
+                    out[o] = (float)(mask_natural[2 * k] * inv);
+                } else {
+                    out[2 * o] = (float)(mask_natural[2 * k] * inv);
+                    out[2 * o + 1] = (float)(mask_natural[2 * k + 1] * inv);
+                }
+            }
+    return out;
+}
+
 // ---- 16-points-per-thread variant (fft_core16.cuh) ---------------------------
 template <class C>
 inline std::vector<cf> build16_tw1() {

@@ -26,6 +26,7 @@ struct HostTables {
 struct FirVariant {
     const char* name;
     int n, threads;
+    int cluster;   // CTAs per thread-block cluster cooperating on one transform (1 = ordinary launch)
     size_t smem;
     fir_kernel_fn cplx, real;
     fir_kernel_fn cplx_i16, real_i16;  // 16-bit PCM in/out (IoI16)
@@ -45,6 +46,7 @@ FirVariant make_variant32(const char* name) {
     v.name = name;
     v.n = C::N;
     v.threads = C::T;
+    v.cluster = 1;
     v.smem = (size_t)C::TILE * sizeof(cf);
     v.cplx = fir_block_kernel<C, cf, MIN_CTAS>;
     v.real = fir_block_kernel<C, float, MIN_CTAS>;
@@ -86,6 +88,7 @@ FirVariant make_variant16(const char* name) {
     v.name = name;
     v.n = C::N;
     v.threads = C::T;
+    v.cluster = 1;
     v.smem = (size_t)C::TILE * sizeof(cf);
     v.cplx = fir16_block_kernel<C, cf, MIN_CTAS>;
     v.real = fir16_block_kernel<C, float, MIN_CTAS>;
@@ -104,6 +107,29 @@ FirVariant make_variant16(const char* name) {
     };
     return v;
 }
+#ifdef ADT_FIR_CLUSTER_IMPL
+// thread-block-cluster transform (fir_cluster.cuh): float32 I/O, store or accumulate
+template <class C, int MIN_CTAS>
+FirVariant make_variant_cluster(const char* name) {
+    FirVariant v{};
+    v.name = name;
+    v.n = C::N;
+    v.threads = C::T;
+    v.cluster = C::CS;
+    v.smem = (size_t)C::TILE * sizeof(cf);
+    v.cplx = fir_cluster_kernel<C, cf, MIN_CTAS, false>;
+    v.real = fir_cluster_kernel<C, float, MIN_CTAS, false>;
+    v.accum_cplx = fir_cluster_kernel<C, cf, MIN_CTAS, true>;
+    v.accum_real = fir_cluster_kernel<C, float, MIN_CTAS, true>;
+    v.build = [](const float* mask, bool real_only, HostTables& out) {
+        out.tw1 = build_tw1<C>();
+        out.tw2 = build_tw2<C>();
+        out.coef_s = permute_mask_cluster<C>(mask, real_only);
+        out.coef_x.clear();
+    };
+    return v;
+}
+#endif
 #endif  // ADT_FIR_VARIANT_IMPL
 
 // one accessor per translation unit (null when the family is not built)
@@ -112,5 +138,7 @@ const FirVariant* fir_variant_p32_8192();
 const FirVariant* fir_variant_p32_16384();
 const FirVariant* fir_variant_p16_4096();
 const FirVariant* fir_variant_p16_8192();
+const FirVariant* fir_variant_c4_32768();   // 4-CTA cluster, N = 32768
+const FirVariant* fir_variant_c2_16384();   // 2-CTA cluster, N = 16384 (A/B against the one-CTA kernel)
 
 }  // namespace adt

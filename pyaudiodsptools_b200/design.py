@@ -15,7 +15,7 @@ import os
 
 import numpy as np
 
-SUPPORTED_FFT = (4096, 8192, 16384)
+SUPPORTED_FFT = (4096, 8192, 16384, 32768)
 
 def filter_length(chunk: int) -> int:
     return chunk // 2 - 1  # EffectFFTFilter.py:22
@@ -83,7 +83,7 @@ class BlockPlan:
 # Measured cost of one FFT point (kernel time per transform point, relative to N = 8192) on B200,
 # gpurun_out/q7: the 4-CTA/SM N = 4096 kernels overlap memory and FP phases best, the 1-CTA/SM
 # N = 16384 kernel worst.  The planner minimises  segments * cost * N / hop.
-_POINT_COST = {4096: 0.82, 8192: 1.00, 16384: 1.36}
+_POINT_COST = {4096: 0.82, 8192: 1.00, 16384: 1.36, 32768: 1.30}
 _ALIGN_SLACK = 64          # worst-case loss of hop to the 32-sample alignment of n0 and hop (plan_block)
 _MAX_SEGMENTS = 64
 

@@ -43,10 +43,13 @@ def test_whole_buffer_matches_reference(gpu_lib, name):
     assert np.max(np.abs(y - arr["y"])) <= MAX_TOL
 
 
-@pytest.mark.parametrize("fft_size,kernel", [(4096, "p16"), (8192, "p16"), (4096, "p32"), (8192, "p32"), (16384, "p32")])
+@pytest.mark.parametrize("fft_size,kernel", [(4096, "p16"), (8192, "p16"), (4096, "p32"), (8192, "p32"), (16384, "p32"),
+                                             (16384, "c2"), (32768, "c4")])
 @pytest.mark.parametrize("name", ["highcut4000_c512_noise", "eq3fft_c512_noise", "lowcut160_default_c1024_noise"])
 def test_every_kernel_variant(gpu_lib, monkeypatch, name, fft_size, kernel):
-    """p16 / p32 = 16 / 32 complex points per thread (fft_core16.cuh / fft_core.cuh), real and complex masks."""
+    """p16 / p32 = 16 / 32 complex points per thread (fft_core16.cuh / fft_core.cuh), c2 / c4 = one transform on a
+    2- / 4-CTA thread-block cluster with the transposition through distributed shared memory (fir_cluster.cuh);
+    real and complex masks."""
     meta, arr = load_golden(name)
     if kernel == "p16" and b"ab_variants=1" not in gpu_lib.adt_version():
         pytest.skip("the p16 A/B family is only in the AB=1 build (ADT_LIB_PATH=.../libadt_b200_ab.so)")
@@ -107,7 +110,7 @@ def test_other_chunk_sizes(gpu_lib, chunk, kind):
     assert rms(ys - y) <= 1e-6
 
 
-@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("seed", range(8))
 def test_engine_with_arbitrary_filters(gpu_lib, seed):
     """The FIR engine is generic (y[m] = sum_k h[k] x[m - D - k]): random non-symmetric / even-length taps,
     every kernel size, against numpy.convolve."""
@@ -116,7 +119,7 @@ def test_engine_with_arbitrary_filters(gpu_lib, seed):
     chunk = [512, 1024, 4096][seed % 3]
     t = int(rng.integers(2, chunk - 4))
     taps = rng.standard_normal(t) / np.sqrt(t)
-    fft = [4096, 8192, 16384][(seed // 2) % 3]
+    fft = [4096, 8192, 16384, 32768][(seed // 2) % 4]
     dev = devices._FirDevice(taps, chunk, channels=3, fft_size=fft)
     assert dev.plan.mask_is_real == bool(t % 2 == 1 and np.allclose(taps, taps[::-1]))
     n = 5 * chunk + 17

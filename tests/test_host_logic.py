@@ -55,7 +55,7 @@ def test_block_plan_reproduces_reference(name):
     assert np.max(np.abs(y - arr["y"])) <= 2e-6
 
 
-@pytest.mark.parametrize("fft_size", [4096, 8192, 16384])
+@pytest.mark.parametrize("fft_size", [4096, 8192, 16384, 32768])
 def test_block_plan_any_fft_size(fft_size):
     meta, arr = load_golden("highcut4000_c1024_noise")
     plan = design.plan_block(_taps_for(meta), design.stream_delay(1024), fft_size)

@@ -17,7 +17,7 @@ __device__ __forceinline__ double round32_int(double v) {
 template <int MODE>
 __global__ void k(double* out, double a, double b, int lanes) {
     if ((int)threadIdx.x >= lanes) return;
-    double y1 = a * threadIdx.x + 0.1, y2 = 0.3, acc = 0.7;
+    double y1 = a * threadIdx.x + 0.1, y2 = 0.3, acc = 0.7, z4 = 0.9;
     long long t0 = clock64();
 #pragma unroll 16
     for (int i = 0; i < N; ++i) {
@@ -39,9 +39,16 @@ __global__ void k(double* out, double a, double b, int lanes) {
             y1 = round32_int(t);
         }
         if (MODE == 7) y1 = (double)(float)((float)y1 * 1.0001f);            // FMUL + conversions, for comparison
+        if (MODE == 8) {   // four INDEPENDENT DMUL chains: per-iteration time = 4 x issue interval if the pipe is narrow
+            y1 = __dmul_rn(y1, b); y2 = __dmul_rn(y2, b); acc = __dmul_rn(acc, b); z4 = __dmul_rn(z4, b);
+        }
+        if (MODE == 9) {   // four independent rounding round trips
+            y1 = (double)__double2float_rn(__dadd_rn(y1, b)); y2 = (double)__double2float_rn(__dadd_rn(y2, b));
+            acc = (double)__double2float_rn(__dadd_rn(acc, b)); z4 = (double)__double2float_rn(__dadd_rn(z4, b));
+        }
     }
     long long t1 = clock64();
-    out[threadIdx.x] = y1 + y2;
+    out[threadIdx.x] = y1 + y2 + acc + z4;
     if (threadIdx.x == 0) out[64] = (double)(t1 - t0) / N;
 }
 
@@ -68,5 +75,7 @@ int main() {
     run<5>("biquad step (DMUL,DADD,DADD,F2F,F2F)", d);
     run<6>("biquad step with integer rounding", d);
     run<7>("F2F + FMUL + F2F", d);
+    run<8>("4 independent DMUL chains (per iteration)", d);
+    run<9>("4 independent DADD + F2F + F2F chains (per iteration)", d);
     return 0;
 }
