@@ -80,10 +80,12 @@ class BlockPlan:
     delay: int
 
 
-# Measured cost of one FFT point (kernel time per transform point, relative to N = 8192) on B200,
-# gpurun_out/q7: the 4-CTA/SM N = 4096 kernels overlap memory and FP phases best, the 1-CTA/SM
-# N = 16384 kernel worst.  The planner minimises  segments * cost * N / hop.
-_POINT_COST = {4096: 0.82, 8192: 1.00, 16384: 1.36, 32768: 1.30}
+# Measured cost of one FFT point (kernel time per transform point, relative to N = 8192) on B200
+# (gpurun_out/q7, r2d): the 4-CTA/SM N = 4096 kernels overlap memory and FP phases best, the 1-CTA/SM
+# N = 16384 kernel is worse, and the 4-CTA-cluster N = 32768 transform is bound by the distributed-shared-
+# memory exchange (~11 B/clk/SM of st.async) — it is chosen only where it saves whole
+# passes (e.g. the 16381-tap EQ at chunk 16384).  The planner minimises  segments * cost * N / hop.
+_POINT_COST = {4096: 0.82, 8192: 1.00, 16384: 1.36, 32768: 2.30}
 _ALIGN_SLACK = 64          # worst-case loss of hop to the 32-sample alignment of n0 and hop (plan_block)
 _MAX_SEGMENTS = 64
 
