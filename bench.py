@@ -543,6 +543,19 @@ def main():
                "api": f"{ctor.__name__}(...).{'process_int16' if i16 else 'process'}(pinned host array)"}
         got = y_host[channels - 1].astype(np.float64) / 32767 if i16 else y_host[channels - 1]
         assert float(np.sqrt(np.mean((got - want) ** 2))) <= (3e-5 if i16 else 1e-5), "e2e parity broken"
+        # the platform's transfer ceiling: the same bytes up and down at the same time on every rank, no kernel
+        ctx.copy_roundtrip(dx, x_host, y_host, dy)
+        barrier(); ctx.sync()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ctx.copy_roundtrip(dx, x_host, y_host, dy)
+        dt_copy = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+        barrier()
+        e2e["transfer_only"] = {
+            "ms_per_step": dt_copy * 1e3, "GBps_per_rank_each_way": x_host.nbytes / dt_copy / 1e9,
+            "fraction_of_e2e_time": dt_copy / dt,
+            "what": "concurrent cudaMemcpyAsync H2D + D2H of the step's bytes on all ranks at once, no kernel: the "
+                    "ceiling the host / PCIe side of this box allows"}
 
     # ---- N > 1: the product's own multi-GPU path: scatter -> kernel -> gather over adt_comm (NCCL) ----------
     scatter_gather = None

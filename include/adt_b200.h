@@ -72,6 +72,10 @@ int adt_memset(adt_ctx* ctx, void* dptr, int value, size_t bytes);
 int adt_memcpy_h2d(adt_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);  /* sync on return */
 int adt_memcpy_d2h(adt_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);  /* sync on return */
 int adt_memcpy_d2d(adt_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes);   /* async */
+/* one H2D and one D2H copy running concurrently on two copy streams; returns when both are complete.  The
+ * platform's transfer ceiling for the *_host entry points (measurement aid for bench.py). */
+int adt_copy_roundtrip_host(adt_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes_h2d, void* dst_host,
+                            const void* src_dev, size_t bytes_d2h);
 
 /* ---- CUDA-event timing on the context's stream (for bench.py) ------------ */
 int adt_event_create(adt_ctx* ctx, adt_event** out);

@@ -51,6 +51,7 @@ PROTOTYPES = {
     "adt_memcpy_h2d": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "adt_memcpy_d2h": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "adt_memcpy_d2d": (C.c_int, [_P, _P, _P, C.c_size_t]),
+    "adt_copy_roundtrip_host": (C.c_int, [_P, _P, _P, C.c_size_t, _P, _P, C.c_size_t]),
     "adt_event_create": (C.c_int, [_P, C.POINTER(_P)]),
     "adt_event_destroy": (C.c_int, [_P]),
     "adt_event_record": (C.c_int, [_P]),
@@ -178,6 +179,11 @@ class Context:
     def d2d(self, dst: int, src: int, nbytes: int):
         """Asynchronous device-to-device copy on the context stream."""
         self.check(self.lib.adt_memcpy_d2d(self.h, dst, src, nbytes))
+
+    def copy_roundtrip(self, dst_dev: int, src_host: np.ndarray, dst_host: np.ndarray, src_dev: int):
+        """H2D of src_host and D2H into dst_host at the same time (two copy streams); blocks until both are done."""
+        self.check(self.lib.adt_copy_roundtrip_host(self.h, dst_dev, src_host.ctypes.data, src_host.nbytes,
+                                                    dst_host.ctypes.data, src_dev, dst_host.nbytes))
 
     def sync(self):
         self.check(self.lib.adt_ctx_sync(self.h))

@@ -244,6 +244,20 @@ extern "C" int adt_memcpy_d2d(adt_ctx* ctx, void* dst, const void* src, size_t b
     return ADT_OK;
 }
 
+// Concurrent H2D and D2H of the given sizes on two copy streams, returns when both are done: the transfer
+// ceiling of this box for a *_host call (bench.py reports it next to the end-to-end number).
+extern "C" int adt_copy_roundtrip_host(adt_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes_h2d, void* dst_host,
+                                       const void* src_dev, size_t bytes_d2h) {
+    if (!ctx || ((!dst_dev || !src_host) && bytes_h2d) || ((!dst_host || !src_dev) && bytes_d2h)) return ADT_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (bytes_h2d) CK(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes_h2d, cudaMemcpyHostToDevice, ctx->copy_stream[0]));
+    if (bytes_d2h) CK(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes_d2h, cudaMemcpyDeviceToHost, ctx->copy_stream[1]));
+    CK(ctx, cudaStreamSynchronize(ctx->copy_stream[0]));
+    CK(ctx, cudaStreamSynchronize(ctx->copy_stream[1]));
+    return ADT_OK;
+}
+
 // ---------------------------------------------------------------------------
 // events
 // ---------------------------------------------------------------------------
