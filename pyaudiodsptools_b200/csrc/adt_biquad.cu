@@ -137,17 +137,14 @@ struct BiquadRound<float, false> {
 template <>
 struct BiquadRound<float, true> {
     static __device__ __forceinline__ double run(double acc, float* out) {
-        long long b = __double_as_longlong(acc);
-        const unsigned e = ((unsigned)(b >> 52)) & 0x7ffu;              // biased float64 exponent
-        if (e - 897u >= 1150u - 897u) {   // outside [2^-126, 2^127): zero, float32-denormal, huge, inf, nan
-            const float f = __double2float_rn(acc);
-            *out = f;
-            return (double)f;
-        }
-        b += 0x0FFFFFFFLL + ((b >> 29) & 1);
+        const long long a = __double_as_longlong(acc);
+        long long b = a + (0x0FFFFFFFLL + ((a >> 29) & 1));               // the chain: shift, and, add, and
         b &= ~0x1FFFFFFFLL;
-        const double r = __longlong_as_double(b);
-        *out = __double2float_rn(r);      // exact (already float32-representable) and off the dependent chain
+        double r = __longlong_as_double(b);
+        const unsigned e = ((unsigned)(a >> 52)) & 0x7ffu;                // biased float64 exponent (off the chain)
+        if (__builtin_expect(e - 897u >= 1150u - 897u, 0))                // outside [2^-126, 2^127): zero, float32-
+            r = (double)__double2float_rn(acc);                           // denormal, huge, inf, nan -> conversion path
+        *out = __double2float_rn(r);      // exact (r is float32-representable) and off the dependent chain
         return r;
     }
 };
@@ -210,8 +207,28 @@ __global__ void __launch_bounds__(96) biquad3_kernel(const T* __restrict__ x, T*
                 y2 = y1; y1 = fb;
             };
             if (w == 32) {
-#pragma unroll 8
-                for (int j = 0; j < 32; ++j) one(j);
+                // Full tile in two phases, because a warp issues in order and nothing else runs on its SM
+                // partition: (A) every feed-forward sum of the tile — independent of the outputs, so its
+                // conversions and products pipeline at full rate; (B) the feedback recurrence alone, whose
+                // per-sample cost is then exactly the dependent chain DMUL -> DSUB -> DSUB -> round.
+                double ff[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const double xin = (double)src[lane][j];
+                    double f = __dmul_rn(k.c[0], x1);
+                    f = __dadd_rn(f, __dmul_rn(k.c[1], x2));
+                    ff[j] = __dadd_rn(f, __dmul_rn(k.c[2], x3));
+                    x3 = x2; x2 = x1; x1 = xin;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    double acc = __dsub_rn(ff[j], __dmul_rn(k.c[3], y1));
+                    acc = __dsub_rn(acc, __dmul_rn(k.c[4], y2));
+                    T out;
+                    const double fb = BiquadRound<T, ROUND_INT>::run(acc, &out);
+                    dst[lane][j] = out;
+                    y2 = y1; y1 = fb;
+                }
             } else {
                 for (int j = 0; j < w; ++j) one(j);
             }

@@ -383,6 +383,15 @@ struct IoF32 {
     typedef float elem;
     ADT_HD static float load(const float* p) { return ld_stream_f32(p); }
     ADT_HD static void store(float* p, float v) { *p = v; }
+    // store only when ok: ONE predicated STG instead of the branch region (BSSY / BRA / BSYNC) the compiler
+    // builds around `if (ok) *p = v` — 32 such regions per thread in the store phase of the FIR kernel
+    ADT_HD static void store_if(bool ok, float* p, float v) {
+#if defined(__CUDA_ARCH__)
+        asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q st.global.f32 [%0], %1;\n}" ::"l"(p), "f"(v), "r"((unsigned)ok) : "memory");
+#else
+        if (ok) *p = v;
+#endif
+    }
 };
 struct IoI16 {
     typedef short elem;
@@ -390,6 +399,9 @@ struct IoI16 {
     ADT_HD static void store(short* p, float v) {
         // numpy's float32 -> int16 astype on x86: truncate toward zero to int32, keep the low 16 bits
         *p = (short)(int)(v * 32767.0f);
+    }
+    ADT_HD static void store_if(bool ok, short* p, float v) {
+        if (ok) store(p, v);
     }
 };
 
@@ -548,8 +560,13 @@ ADT_HD void store_slice_impl(const cf* v, int t, typename IO::elem* __restrict__
                 if (ok) pa[off] += z.x;
                 if (ok && pb) pb[off] += z.y;
             } else {
-                if (ok) IO::store(pa + off, (SHAPED ? fir_shape(shape, z.x) : z.x));
-                if (ok && pb) IO::store(pb + off, (SHAPED ? fir_shape(shape, z.y) : z.y));
+                if constexpr (SHAPED) {
+                    if (ok) IO::store(pa + off, fir_shape(shape, z.x));
+                    if (ok && pb) IO::store(pb + off, fir_shape(shape, z.y));
+                } else {
+                    IO::store_if(ok, pa + off, z.x);
+                    IO::store_if(ok && pb, pb + off, z.y);
+                }
             }
         });
     });
