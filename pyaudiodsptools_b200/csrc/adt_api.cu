@@ -131,7 +131,7 @@ extern "C" int adt_ctx_create(int device, adt_ctx** out) {
         if (!v) continue;
         for (fir_kernel_fn f : {v->cplx, v->real, v->cplx_i16, v->real_i16, v->persist_cplx, v->persist_real,
                                 v->shaped_cplx, v->shaped_real, v->split_int_cplx, v->split_int_real,
-                                v->split_edge_cplx, v->split_edge_real, v->tma_cplx, v->tma_real, v->accum_cplx,
+                                v->split_edge_cplx, v->split_edge_real, v->tma_cplx, v->tma_real, v->vt2_cplx, v->vt2_real, v->accum_cplx,
                                 v->accum_real}) {
             if (!f) continue;
             e = cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v->smem);
@@ -386,9 +386,15 @@ static int fir_launch_seg(adt_fir* f, FirSeg& sg, bool accum, cudaStream_t s, co
                              shaped ? "store-epilogue" : i16 ? "int16" : "such");
     static const int tma_mode = getenv("ADT_FIR_TMA") ? atoi(getenv("ADT_FIR_TMA")) : 0;   // A/B: TMA-fed window load
     if (tma_mode && !shaped && !i16 && !accum && sg.var->tma_real) k = sg.d.mask_is_real ? sg.var->tma_real : sg.var->tma_cplx;
+    static const int vt_mode = getenv("ADT_FIR_VT") ? atoi(getenv("ADT_FIR_VT")) : 0;   // A/B: two virtual threads per thread
+    int threads = sg.var->threads;
+    if (vt_mode == 2 && !shaped && !i16 && !accum && sg.var->vt2_real) {
+        k = sg.d.mask_is_real ? sg.var->vt2_real : sg.var->vt2_cplx;
+        threads /= 2;
+    }
     if (sg.resident_ctas == 0) {  // CTAs in flight at once = how far ahead the L2 prefetch looks
         int per_sm = 0, sms = 0;
-        CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, sg.var->threads, sg.var->smem));
+        CK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k, threads, sg.var->smem));
         CK(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
         sg.resident_ctas = per_sm > 0 ? per_sm * sms : sms;
     }
@@ -458,7 +464,7 @@ static int fir_launch_seg(adt_fir* f, FirSeg& sg, bool accum, cudaStream_t s, co
         ctx->launches++;
         return ADT_OK;
     }
-    k<<<grid, sg.var->threads, sg.var->smem, s>>>(a, ex);
+    k<<<grid, threads, sg.var->smem, s>>>(a, ex);
     CK(ctx, cudaGetLastError());
     ctx->launches++;
     return ADT_OK;

@@ -208,21 +208,24 @@ __global__ void __launch_bounds__(96) biquad3_kernel(const T* __restrict__ x, T*
             };
             if (w == 32) {
                 // Full tile in two phases, because a warp issues in order and nothing else runs on its SM
-                // partition: (A) every feed-forward sum of the tile — independent of the outputs, so its
-                // conversions and products pipeline at full rate; (B) the feedback recurrence alone, whose
-                // per-sample cost is then exactly the dependent chain DMUL -> DSUB -> DSUB -> round.
-                double ff[32];
+                // partition: (A) every feed-forward sum of the tile — independent of the outputs, so its loads,
+                // conversions and products pipeline at full rate — parked in shared memory; (B) the feedback
+                // recurrence alone, whose per-sample cost is then the dependent chain DMUL -> DSUB -> DSUB ->
+                // round.  The shared-memory hand-over is what keeps the compiler from re-interleaving the two
+                // (it otherwise schedules each conversion right before its consumer and the warp stalls on it).
+                double (*ffs)[33] = reinterpret_cast<double (*)[33]>(bq_smem + 6 * sizeof(Tile)) + band * 32;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const double xin = (double)src[lane][j];
                     double f = __dmul_rn(k.c[0], x1);
                     f = __dadd_rn(f, __dmul_rn(k.c[1], x2));
-                    ff[j] = __dadd_rn(f, __dmul_rn(k.c[2], x3));
+                    ffs[lane][j] = __dadd_rn(f, __dmul_rn(k.c[2], x3));
                     x3 = x2; x2 = x1; x1 = xin;
                 }
+                __syncwarp();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    double acc = __dsub_rn(ff[j], __dmul_rn(k.c[3], y1));
+                    double acc = __dsub_rn(ffs[lane][j], __dmul_rn(k.c[3], y1));
                     acc = __dsub_rn(acc, __dmul_rn(k.c[4], y2));
                     T out;
                     const double fb = BiquadRound<T, ROUND_INT>::run(acc, &out);
@@ -364,7 +367,7 @@ extern "C" int adt_biquad_chain_apply_dev(adt_biquad* low, adt_biquad* mid, adt_
     const unsigned grid = (unsigned)((low->n_channels + 31) / 32);
     static const int round_int = getenv("ADT_BIQUAD_ROUND_INT") ? atoi(getenv("ADT_BIQUAD_ROUND_INT")) : ADT_BIQUAD_ROUND_INT_DEFAULT;
     if (low->f64) {
-        const size_t smem = 6 * 32 * 33 * sizeof(double);
+        const size_t smem = 6 * 32 * 33 * sizeof(double) + 3 * 32 * 33 * sizeof(double);
         static bool attr_done = false;
         if (!attr_done) {
             ADT_CK(ctx, cudaFuncSetAttribute((const void*)biquad3_kernel<double, false>,
@@ -374,7 +377,15 @@ extern "C" int adt_biquad_chain_apply_dev(adt_biquad* low, adt_biquad* mid, adt_
         biquad3_kernel<double, false><<<grid, 96, smem, ctx->stream>>>((const double*)x, (double*)y, pitch, n,
                                                                       low->n_channels, a);
     } else {
-        const size_t smem = 6 * 32 * 33 * sizeof(float);
+        const size_t smem = 6 * 32 * 33 * sizeof(float) + 3 * 32 * 33 * sizeof(double);   // 50 688 B: opt-in size
+        static bool attr_f32 = false;
+        if (!attr_f32) {
+            ADT_CK(ctx, cudaFuncSetAttribute((const void*)biquad3_kernel<float, true>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ADT_CK(ctx, cudaFuncSetAttribute((const void*)biquad3_kernel<float, false>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_f32 = true;
+        }
         if (round_int)
             biquad3_kernel<float, true><<<grid, 96, smem, ctx->stream>>>((const float*)x, (float*)y, pitch, n,
                                                                         low->n_channels, a);

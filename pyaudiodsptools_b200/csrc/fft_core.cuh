@@ -367,6 +367,9 @@ struct FirGeom {
 // Streaming read (window samples are used once per CTA): read-only path, no L1 allocation, so the
 // 64 KB windows do not evict the mask / twiddle tables that every CTA re-reads from L1.  Plain (non
 // volatile) asm: the loads stay freely schedulable.  Compile-time switch, OFF by default (measured slower).
+#ifndef ADT_STORE_PRED
+#define ADT_STORE_PRED 0     /* 1: one predicated STG (inline PTX) instead of the branch region around `if (ok) *p = v`: 130 fewer instructions per thread but measured 1.4 % SLOWER on the same box (gpurun_out/r2h) -> off */
+#endif
 #ifndef ADT_STREAM_LOADS
 #define ADT_STREAM_LOADS 0   /* measured on B200: no_allocate loads are 2 % slower than ordinary allocating loads */
 #endif
@@ -386,8 +389,10 @@ struct IoF32 {
     // store only when ok: ONE predicated STG instead of the branch region (BSSY / BRA / BSYNC) the compiler
     // builds around `if (ok) *p = v` — 32 such regions per thread in the store phase of the FIR kernel
     ADT_HD static void store_if(bool ok, float* p, float v) {
-#if defined(__CUDA_ARCH__)
-        asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q st.global.f32 [%0], %1;\n}" ::"l"(p), "f"(v), "r"((unsigned)ok) : "memory");
+#if defined(__CUDA_ARCH__) && ADT_STORE_PRED
+        // no "memory" clobber: the kernel never reads what it stores, so the compiler stays free to hoist the
+        // next butterfly's shared-memory loads above these stores
+        asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q st.global.f32 [%0], %1;\n}" ::"l"(p), "f"(v), "r"((unsigned)ok));
 #else
         if (ok) *p = v;
 #endif

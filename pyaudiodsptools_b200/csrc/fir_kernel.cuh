@@ -119,6 +119,41 @@ __global__ void __launch_bounds__(C::T, MIN_CTAS) fir_block_kernel(const FirKern
     store_slice<C, IO, SHAPED, ACCUM>(v, t, it.ya, it.yb, it.m0, a.g, ex.shape);
 }
 
+// TWO VIRTUAL THREADS PER THREAD (A/B, ADT_FIR_VT=2): the CTA has T/2 threads and every phase runs twice, for
+// virtual thread ids t and t + T/2.  All exchanges are in place and separated by the same barriers, so the
+// result is identical; what changes is the schedule: 3 CTAs of 128 threads per SM instead of 2 of 256 (three
+// independent phase positions per SM), up to 168 registers per thread, and two independent butterfly streams
+// inside each thread whose shared-memory and FP instructions the compiler can interleave.
+template <class C, class MaskT, int MIN_CTAS>
+__global__ void __launch_bounds__(C::T / 2, MIN_CTAS) fir_vt2_kernel(const FirKernelArgs a, const FirExtra ex) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cf* tile = reinterpret_cast<cf*>(smem_raw);
+    constexpr int H = C::T / 2;
+    const int t0 = threadIdx.x, t1 = threadIdx.x + H;
+    const long long item = blockIdx.x;
+    const FirItem<float> it = fir_item<float>(a, item);
+    cf v[32], w[32];
+    load_window<C, IoF32>(v, t0, it.xa, it.xb, it.ws, a.g.n_in);
+    load_window<C, IoF32>(w, t1, it.xa, it.xb, it.ws, a.g.n_in);
+    fir_prefetch_l2<C::N, C::T, float>(a, item, t0);
+    fwd_stage1<C>(v, t0, a.tw1, tile);
+    fwd_stage1<C>(w, t1, a.tw1, tile);
+    __syncthreads();
+    fwd_stage2<C>(v, t0, a.tw2, tile);
+    fwd_stage2<C>(w, t1, a.tw2, tile);
+    __syncwarp();  // virtual warps w and w + WARPS/2 live in the same physical warp: stage 3 reads its own rows
+    mid_stage3<C, MaskT>(v, t0, reinterpret_cast<const MaskT*>(a.mask), tile);
+    mid_stage3<C, MaskT>(w, t1, reinterpret_cast<const MaskT*>(a.mask), tile);
+    __syncwarp();
+    inv_stage2<C>(v, t0, a.tw2, tile);
+    inv_stage2<C>(w, t1, a.tw2, tile);
+    __syncthreads();
+    inv_stage1<C>(v, t0, a.tw1, tile);
+    store_slice<C, IoF32, false>(v, t0, it.ya, it.yb, it.m0, a.g, ex.shape);
+    inv_stage1<C>(w, t1, a.tw1, tile);
+    store_slice<C, IoF32, false>(w, t1, it.ya, it.yb, it.m0, a.g, ex.shape);
+}
+
 // TMA-FED variant (A/B, ADT_FIR_TMA=1): the two row windows of an interior item are brought
 // into the (not yet used) tile by the bulk-copy engine — one cp.async.bulk.shared::cluster.global per row,
 // completion on an mbarrier (SASS: UBLKCP + SYNCS) — and stage 1 reads its 32 points from shared memory
