@@ -149,21 +149,12 @@ struct BiquadRound<float, true> {
     }
 };
 
-// shared memory of biquad3_kernel: 5 double tiles (input, low->mid x2, mid->high x2), 3 feed-forward buffers
-// (one per band), 1 output tile of T
-#define ADT_BQ3_SMEM(T) (8 * 32 * 33 * sizeof(double) + 32 * 33 * sizeof(T))
-
 template <typename T, bool ROUND_INT>
 __global__ void __launch_bounds__(96) biquad3_kernel(const T* __restrict__ x, T* __restrict__ y, long long pitch,
                                                      long long n, int n_channels, Biquad3Args a) {
     extern __shared__ __align__(16) unsigned char bq_smem[];
-    // Samples travel between the bands as float64 (the value a band feeds back is already the float64 image of
-    // its float32 output, so the next band needs no conversion); only the global boundary is T.
-    typedef double TileD[32][33];
-    typedef T TileT[32][33];
-    TileD* tiles = reinterpret_cast<TileD*>(bq_smem);          // [0] input, [1..2] low->mid, [3..4] mid->high
-    volatile double (*ffs)[33] = reinterpret_cast<volatile double (*)[33]>(bq_smem + 5 * sizeof(TileD)) + (threadIdx.x >> 5) * 32;
-    TileT& outt = *reinterpret_cast<TileT*>(bq_smem + 8 * sizeof(TileD));
+    typedef T Tile[32][33];
+    Tile* tiles = reinterpret_cast<Tile*>(bq_smem);   // [0] input, [1..2] low->mid, [3..4] mid->high, [5] output
     const int lane = threadIdx.x & 31, band = threadIdx.x >> 5;
     const int c0 = blockIdx.x * 32;
     const int ch = c0 + lane;
@@ -188,69 +179,65 @@ __global__ void __launch_bounds__(96) biquad3_kernel(const T* __restrict__ x, T*
         const bool active = tile >= 0 && tile < n_tiles;
         const long long base = tile * 32;
         const int w = active ? (int)min((long long)32, n - base) : 0;
-        TileD& src = band == 0 ? tiles[0] : tiles[(band == 1 ? 1 : 3) + (int)(tile & 1)];
-        TileD& dst = tiles[(band == 0 ? 1 : 3) + (int)(tile & 1)];     // unused by band 2
+        Tile& src = band == 0 ? tiles[0] : tiles[(band == 1 ? 1 : 3) + (int)(tile & 1)];
+        Tile& dst = band == 2 ? tiles[5] : tiles[(band == 0 ? 1 : 3) + (int)(tile & 1)];
         if (band == 0 && active) {
-            // transpose the tile into shared memory, converting on the way: 32 independent conversions
 #pragma unroll
-            for (int i = 0; i < 32; ++i) src[i][lane] = (double)nxt[i];
+            for (int i = 0; i < 32; ++i) src[i][lane] = nxt[i];
             __syncwarp();
             const long long nb = base + 32;
 #pragma unroll
             for (int i = 0; i < 32; ++i) nxt[i] = (i < rows && nb + lane < n) ? xr[(long long)i * pitch + nb] : T(0);
         }
         if (active && live) {
-            auto emit = [&](int j, double fb, T out) {
-                if (band == 2)
-                    outt[lane][j] = out;
-                else
-                    dst[lane][j] = fb;
+            // Full tiles run a fixed 32-iteration loop, unrolled so that the loads, the float -> double
+            // conversions and the feed-forward sum of later samples are issued while the feedback chain
+            // (DMUL -> DSUB -> DSUB -> round) of earlier ones is still in flight.
+            auto one = [&](int j) {
+                const double xin = (double)src[lane][j];
+                double ff = __dmul_rn(k.c[0], x1);
+                ff = __dadd_rn(ff, __dmul_rn(k.c[1], x2));
+                ff = __dadd_rn(ff, __dmul_rn(k.c[2], x3));
+                double acc = __dsub_rn(ff, __dmul_rn(k.c[3], y1));
+                acc = __dsub_rn(acc, __dmul_rn(k.c[4], y2));
+                T out;
+                const double fb = BiquadRound<T, ROUND_INT>::run(acc, &out);
+                dst[lane][j] = out;
+                x3 = x2; x2 = x1; x1 = xin;
+                y2 = y1; y1 = fb;
             };
             if (w == 32) {
                 // Full tile in two phases, because a warp issues in order and nothing else runs on its SM
-                // partition: (A) every feed-forward sum of the tile — independent of the outputs, so it pipelines
-                // at full rate — parked in shared memory; (B) the feedback recurrence alone, whose per-sample cost
-                // is then the dependent chain DMUL -> DSUB -> DSUB -> round.  The hand-over buffer is volatile so
-                // that all its stores precede all its loads (the compiler otherwise re-interleaves the phases);
-                // every lane re-reads only what it wrote, so no barrier is needed.
+                // partition: (A) every feed-forward sum of the tile — independent of the outputs, so its
+                // conversions and products pipeline at full rate; (B) the feedback recurrence alone, whose
+                // per-sample cost is then exactly the dependent chain DMUL -> DSUB -> DSUB -> round.
+                double ff[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const double xin = src[lane][j];
+                    const double xin = (double)src[lane][j];
                     double f = __dmul_rn(k.c[0], x1);
                     f = __dadd_rn(f, __dmul_rn(k.c[1], x2));
-                    ffs[lane][j] = __dadd_rn(f, __dmul_rn(k.c[2], x3));
+                    ff[j] = __dadd_rn(f, __dmul_rn(k.c[2], x3));
                     x3 = x2; x2 = x1; x1 = xin;
                 }
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    double acc = __dsub_rn(ffs[lane][j], __dmul_rn(k.c[3], y1));
+                    double acc = __dsub_rn(ff[j], __dmul_rn(k.c[3], y1));
                     acc = __dsub_rn(acc, __dmul_rn(k.c[4], y2));
                     T out;
                     const double fb = BiquadRound<T, ROUND_INT>::run(acc, &out);
-                    emit(j, fb, out);
+                    dst[lane][j] = out;
                     y2 = y1; y1 = fb;
                 }
             } else {
-                for (int j = 0; j < w; ++j) {
-                    const double xin = src[lane][j];
-                    double acc = __dmul_rn(k.c[0], x1);
-                    acc = __dadd_rn(acc, __dmul_rn(k.c[1], x2));
-                    acc = __dadd_rn(acc, __dmul_rn(k.c[2], x3));
-                    acc = __dsub_rn(acc, __dmul_rn(k.c[3], y1));
-                    acc = __dsub_rn(acc, __dmul_rn(k.c[4], y2));
-                    T out;
-                    const double fb = BiquadRound<T, ROUND_INT>::run(acc, &out);
-                    emit(j, fb, out);
-                    x3 = x2; x2 = x1; x1 = xin;
-                    y2 = y1; y1 = fb;
-                }
+                for (int j = 0; j < w; ++j) one(j);
             }
         }
         if (band == 2 && active) {
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-                if (i < rows && lane < w) yr[(long long)i * pitch + base] = outt[i][lane];
+                if (i < rows && lane < w) yr[(long long)i * pitch + base] = dst[i][lane];
         }
         __syncthreads();   // hand the tiles over: band b's output of this step is band b+1's input of the next
     }
@@ -376,25 +363,25 @@ extern "C" int adt_biquad_chain_apply_dev(adt_biquad* low, adt_biquad* mid, adt_
     }
     const unsigned grid = (unsigned)((low->n_channels + 31) / 32);
     static const int round_int = getenv("ADT_BIQUAD_ROUND_INT") ? atoi(getenv("ADT_BIQUAD_ROUND_INT")) : ADT_BIQUAD_ROUND_INT_DEFAULT;
-    static bool attr_done = false;
-    if (!attr_done) {   // > 48 KB of dynamic shared memory is opt-in
-        ADT_CK(ctx, cudaFuncSetAttribute((const void*)biquad3_kernel<double, false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ADT_BQ3_SMEM(double)));
-        ADT_CK(ctx, cudaFuncSetAttribute((const void*)biquad3_kernel<float, true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ADT_BQ3_SMEM(float)));
-        ADT_CK(ctx, cudaFuncSetAttribute((const void*)biquad3_kernel<float, false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ADT_BQ3_SMEM(float)));
-        attr_done = true;
+    if (low->f64) {
+        const size_t smem = 6 * 32 * 33 * sizeof(double);
+        static bool attr_done = false;
+        if (!attr_done) {
+            ADT_CK(ctx, cudaFuncSetAttribute((const void*)biquad3_kernel<double, false>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_done = true;
+        }
+        biquad3_kernel<double, false><<<grid, 96, smem, ctx->stream>>>((const double*)x, (double*)y, pitch, n,
+                                                                      low->n_channels, a);
+    } else {
+        const size_t smem = 6 * 32 * 33 * sizeof(float);
+        if (round_int)
+            biquad3_kernel<float, true><<<grid, 96, smem, ctx->stream>>>((const float*)x, (float*)y, pitch, n,
+                                                                        low->n_channels, a);
+        else
+            biquad3_kernel<float, false><<<grid, 96, smem, ctx->stream>>>((const float*)x, (float*)y, pitch, n,
+                                                                         low->n_channels, a);
     }
-    if (low->f64)
-        biquad3_kernel<double, false><<<grid, 96, ADT_BQ3_SMEM(double), ctx->stream>>>((const double*)x, (double*)y, pitch, n,
-                                                                                      low->n_channels, a);
-    else if (round_int)
-        biquad3_kernel<float, true><<<grid, 96, ADT_BQ3_SMEM(float), ctx->stream>>>((const float*)x, (float*)y, pitch, n,
-                                                                                   low->n_channels, a);
-    else
-        biquad3_kernel<float, false><<<grid, 96, ADT_BQ3_SMEM(float), ctx->stream>>>((const float*)x, (float*)y, pitch, n,
-                                                                                    low->n_channels, a);
     ADT_CK(ctx, cudaGetLastError());
     ctx->launches++;
     return ADT_OK;
