@@ -49,7 +49,7 @@ os.environ.pop("ADT_FIR_KERNEL", None)
 # a partitioned (segmented) filter: chunk 32768 -> 16383 taps in tap segments, store + accumulate kernels
 fs, c = 44100, 32768
 adt.config.initialize(fs, c)
-dev = adt.CreateLowCutFilter(800, channels=2)
+dev = adt.CreateLowCutFilter(800, channels=2, fft_size=16384)      # forced N: 3 tap segments, 2 accumulating
 xs = rng.uniform(-1, 1, (2, 2 * c + 50)).astype(np.float32)
 ys = dev.process(xs)
 from scipy.signal import fftconvolve
