@@ -53,5 +53,9 @@ def gpu_lib():
     lib = _native.load()
     n = _native.device_count()
     if n < 1:
-        pytest.fail("gpu-marked test running without a CUDA device")
+        # a plain `pytest tests` on a CPU box skips the GPU tier; where a GPU is expected (the driver's
+        # `-m gpu` run) set ADT_REQUIRE_GPU=1 to turn a missing device into a failure instead of a skip
+        if os.environ.get("ADT_REQUIRE_GPU") == "1":
+            pytest.fail("gpu-marked test running without a CUDA device")
+        pytest.skip("no CUDA device (GPU tier; set ADT_REQUIRE_GPU=1 to fail instead)")
     return lib
