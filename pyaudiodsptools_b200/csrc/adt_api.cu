@@ -16,6 +16,10 @@
 #define CK ADT_CK
 #include "fir_variants.cuh"
 
+#ifndef ADT_FIR_PP_DEFAULT
+#define ADT_FIR_PP_DEFAULT 0   /* ping-pong schedule (fir_pingpong.cuh) as the default for sizes that have it */
+#endif
+
 using namespace adt;
 
 // ---------------------------------------------------------------------------
@@ -139,6 +143,13 @@ extern "C" int adt_ctx_create(int device, adt_ctx** out) {
                 e = cudaFuncSetAttribute((const void*)f, cudaFuncAttributePreferredSharedMemoryCarveout,
                                          atoi(getenv("ADT_FIR_CARVEOUT")));
             if (e != cudaSuccess) {
+                delete ctx;
+                return ADT_ERR_CUDA;
+            }
+        }
+        for (fir_kernel_fn f : {v->pp_cplx, v->pp_real}) {   // two groups, two tiles per CTA
+            if (!f) continue;
+            if (cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * v->smem)) != cudaSuccess) {
                 delete ctx;
                 return ADT_ERR_CUDA;
             }
@@ -445,6 +456,23 @@ static int fir_launch_seg(adt_fir* f, FirSeg& sg, bool accum, cudaStream_t s, co
             }
             return ADT_OK;
         }
+    }
+    // ping-pong schedule: one persistent CTA of two groups per SM; the work counter starts at the first unclaimed item
+    static const int pp_mode = getenv("ADT_FIR_PP") ? atoi(getenv("ADT_FIR_PP")) : ADT_FIR_PP_DEFAULT;
+    fir_kernel_fn kpp = sg.d.mask_is_real ? sg.var->pp_real : sg.var->pp_cplx;
+    if (pp_mode && kpp && !i16 && !shaped && !accum && !persistent && sg.var->cluster == 1 && vt_mode != 2 && !tma_mode) {
+        int sms = 0;
+        CK(ctx, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+        long long ctas = (a.n_items + 1) / 2;
+        if (ctas > sms) ctas = sms;
+        if (!f->d_counter) CK(ctx, cudaMalloc((void**)&f->d_counter, (ADT_COPY_STREAMS + 1) * sizeof(unsigned int)));
+        fir_set_counter<<<1, 1, 0, s>>>(f->d_counter + slot, (unsigned)(2 * ctas));
+        ctx->launches++;
+        ex.work_counter = f->d_counter + slot;
+        kpp<<<(unsigned)ctas, 2 * sg.var->threads, 2 * sg.var->smem, s>>>(a, ex);
+        CK(ctx, cudaGetLastError());
+        ctx->launches++;
+        return ADT_OK;
     }
     if (sg.var->cluster > 1) {   // one thread-block cluster per work item
         if (a.n_items * sg.var->cluster > 0x7fffffffLL)

@@ -1,5 +1,7 @@
 // fir_k8192.cu — kernels of the N = 8192 (256 threads, 2 CTAs/SM; the headline kernel) transform (its own translation unit: sizes compile in parallel).
 #define ADT_FIR_VARIANT_IMPL
+#define ADT_FIR_PINGPONG_IMPL
+#include "fir_pingpong.cuh"
 #include "fir_variants.cuh"
 
 namespace adt {

@@ -35,6 +35,7 @@ struct FirVariant {
     fir_kernel_fn split_int_cplx, split_int_real, split_edge_cplx, split_edge_real;  // split launch (p32) or null
     fir_kernel_fn tma_cplx, tma_real;          // TMA-fed window load (A/B, ADT_FIR_TMA=1) or null
     fir_kernel_fn vt2_cplx, vt2_real;          // two virtual threads per thread, T/2 threads per CTA (A/B, ADT_FIR_VT=2) or null
+    fir_kernel_fn pp_cplx, pp_real;            // ping-pong schedule (fir_pingpong.cuh): 2 groups per CTA, persistent, or null
     fir_kernel_fn accum_cplx, accum_real;      // y += result: tap segments 1.. of a partitioned (long) filter, or null
     void (*build)(const float* mask, bool real_only, HostTables& out);
 };
@@ -65,6 +66,13 @@ FirVariant make_variant32(const char* name) {
     v.accum_real = fir_block_kernel<C, float, MIN_CTAS, IoF32, false, true>;
     v.tma_cplx = v.tma_real = nullptr;
     v.vt2_cplx = v.vt2_real = nullptr;
+    v.pp_cplx = v.pp_real = nullptr;
+#ifdef ADT_FIR_PINGPONG_IMPL
+    if constexpr (TMA && C::T == 256) {
+        v.pp_cplx = fir_pingpong_kernel<C, cf>;
+        v.pp_real = fir_pingpong_kernel<C, float>;
+    }
+#endif
     if constexpr (TMA) {
         v.tma_cplx = fir_tma_kernel<C, cf, MIN_CTAS>;
         v.tma_real = fir_tma_kernel<C, float, MIN_CTAS>;
@@ -104,6 +112,7 @@ FirVariant make_variant16(const char* name) {
     v.split_int_cplx = v.split_int_real = v.split_edge_cplx = v.split_edge_real = nullptr;
     v.tma_cplx = v.tma_real = nullptr;
     v.vt2_cplx = v.vt2_real = nullptr;
+    v.pp_cplx = v.pp_real = nullptr;
     v.accum_cplx = v.accum_real = nullptr;
     v.build = [](const float* mask, bool real_only, HostTables& out) {
         out.tw1 = build16_tw1<C>();
