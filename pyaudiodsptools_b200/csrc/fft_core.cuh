@@ -374,9 +374,35 @@ struct FirGeom {
 #define ADT_STREAM_LOADS 0   /* measured on B200: no_allocate loads are 2 % slower than ordinary allocating loads */
 #endif
 ADT_HD float ld_stream_f32(const float* p) {
-#if defined(__CUDA_ARCH__) && ADT_STREAM_LOADS
+#if defined(__CUDA_ARCH__) && ADT_STREAM_LOADS == 1
     float v;
     asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+#elif defined(__CUDA_ARCH__) && ADT_STREAM_LOADS == 2
+    float v;
+    asm("ld.global.nc.L1::evict_first.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+#else
+    return *p;
+#endif
+}
+// Mask table loads (re-read by every CTA): optionally ask L1 to keep them (A/B, ADT_MASK_EVICT_LAST)
+#ifndef ADT_MASK_EVICT_LAST
+#define ADT_MASK_EVICT_LAST 0
+#endif
+ADT_HD float ld_mask(const float* p) {
+#if defined(__CUDA_ARCH__) && ADT_MASK_EVICT_LAST
+    float v;
+    asm("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+#else
+    return *p;
+#endif
+}
+ADT_HD cf ld_mask(const cf* p) {
+#if defined(__CUDA_ARCH__) && ADT_MASK_EVICT_LAST
+    cf v;
+    asm("ld.global.nc.L1::evict_last.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
     return v;
 #else
     return *p;
@@ -498,7 +524,7 @@ ADT_HD void mid_stage3(cf* v, int t, const MaskT* __restrict__ mask, cf* tile) {
     static_for<0, 32>([&](auto K) { constexpr int r2 = decltype(K)::value; v[r2] = row[r2]; });
     dft<32, -1>(v);
     cf y[32];
-    masked_idft32<MaskT>(v, y, [&](auto K) { return mask[decltype(K)::value * C::T + t]; });
+    masked_idft32<MaskT>(v, y, [&](auto K) { return ld_mask(mask + decltype(K)::value * C::T + t); });
     static_for<0, 32>([&](auto K) { constexpr int r2 = decltype(K)::value; row[r2] = y[brev<32>(r2)]; });
 }
 
