@@ -315,6 +315,13 @@ def measure_secondary(adt, ctx, name, local_rank, peak, passes=10):
         for _ in range(passes):
             run()
         e1.record()
+        ms_burst = e0.elapsed_ms(e1) / passes          # a short burst, still at boost clocks
+        # ... then ~0.6 s of back-to-back passes, like the headline: the sustained figure under the power cap
+        passes = max(passes, int(600.0 / max(ms_burst, 1e-3)))
+        e0.record()
+        for _ in range(passes):
+            run()
+        e1.record()
         ms = e0.elapsed_ms(e1) / passes
         yrow = np.empty((1, n_out), np.float32)
         ctx.d2h(yrow, dy + (channels - 1) * n_out * 4)
@@ -323,7 +330,9 @@ def measure_secondary(adt, ctx, name, local_rank, peak, passes=10):
         ctx.free(dx); ctx.free(dy)
     gbs = 8.0 * channels * n_out / (ms * 1e-3) / 1e9
     return {"workload": name, "what": desc, "ms_per_pass": ms, "Msamples_s": channels * n_out / (ms * 1e-3) / 1e6,
-            "GBps": gbs, "frac": gbs / peak, "fft_size": dev.plan.fft_size, "hop": dev.plan.hop,
+            "GBps": gbs, "frac": gbs / peak, "ms_per_pass_burst": ms_burst,
+            "frac_burst": 8.0 * channels * n_out / (ms_burst * 1e-3) / 1e9 / peak,
+            "fft_size": dev.plan.fft_size, "hop": dev.plan.hop,
             "segments": getattr(dev, "n_segments", 1), "mask": "real" if dev.plan.mask_is_real else "complex",
             "parity_rms_vs_oracle": err, "passes": passes}
 

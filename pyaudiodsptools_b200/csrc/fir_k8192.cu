@@ -4,9 +4,14 @@
 #include "fir_pingpong.cuh"
 #include "fir_variants.cuh"
 
+// resident CTAs per SM the kernels are compiled for (__launch_bounds__ -> register budget)
+#ifndef ADT_CTAS_8192
+#define ADT_CTAS_8192 2
+#endif
+
 namespace adt {
 const FirVariant* fir_variant_p32_8192() {
-    static const FirVariant v = make_variant32<FirCfg<16, 16>, 2, false, true>("p32");
+    static const FirVariant v = make_variant32<FirCfg<16, 16>, ADT_CTAS_8192, false, true>("p32");
     return &v;
 }
 }  // namespace adt
