@@ -82,6 +82,7 @@ const FirVariant* const* all_variants(int* count) {
         fir_variant_p32_16384(),  // N = 16384, 512 threads, 1 CTA/SM
         fir_variant_c4_32768(),   // N = 32768, 4-CTA cluster x 256 threads, DSMEM exchange
         fir_variant_c2_16384(),   // N = 16384, 2-CTA cluster (ADT_FIR_KERNEL=c2)
+        fir_variant_b2_16384(),   // N = 16384, 2-CTA cluster, bulk DSMEM exchange (ADT_FIR_KERNEL=b2)
         fir_variant_p16_4096(),   // A/B family, null unless built with AB=1
         fir_variant_p16_8192(),
     };

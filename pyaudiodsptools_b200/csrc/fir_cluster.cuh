@@ -77,6 +77,8 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     }
 }
 
+__device__ __forceinline__ cf tw1_at(const cf* __restrict__ tw1, int r) { return tw1[r]; }
+
 // ---- forward stage 1: DFT_N1 down this thread's columns, twiddle, push to the owner of each sub-transform ----
 // tcol = thread index + first column of the CTA (a multiple of 32, so the lane is unchanged).
 template <class C>
@@ -189,6 +191,119 @@ __global__ void __launch_bounds__(C::T, MIN_CTAS) fir_cluster_kernel(const FirKe
     twiddle_idft<C::N2, C::B2>(v, a.tw2[t & 31]);
     mbar_wait(freed_l, 0);                                 // every tile of the cluster may be overwritten now
     cl_inv_stage2_push<C>(v, t, rank, tile_at, full_at);
+    mbar_wait(full_l, 1);
+    cl_inv_stage1<C>(v, t, tcol, a.tw1, tile);
+    store_slice<C, IoF32, false, ACCUM>(v, tcol, it.ya, it.yb, it.m0, a.g, ex.shape);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 2-CTA cluster with a BULK distributed-shared-memory exchange (fir_cluster2b_kernel).
+//
+// The st.async version above issues 32 remote 8-byte stores per thread and exchange and is bound by their
+// throughput (~11 B/clk/SM).  Here the half of a CTA's stage-1 results that belongs to the
+// other CTA is first written — in exactly the destination's tile layout — into a 33 KB staging buffer in the
+// CTA's own shared memory (ordinary STS, the same number of stores as writing the tile), and then handed to
+// the bulk-copy (TMA) engine: 8 x cp.async.bulk.shared::cluster.shared::cta of 4224 bytes (16 tile rows each),
+// completing on the destination CTA's mbarrier.  The threads are free as soon as the copies are issued, and the
+// other CTA resident on the SM computes while the engine moves the data.
+// Tile 67.6 KB + staging 33.8 KB = 101.4 KB per CTA -> still 2 CTAs per SM.
+template <class C>
+struct Cluster2Layout {
+    static_assert(C::CS == 2, "bulk exchange is written for 2-CTA clusters");
+    static constexpr int CHUNK_ROWS = C::N2L;                                   // rows of one k1 block that one CTA fills
+    static constexpr unsigned CHUNK_BYTES = CHUNK_ROWS * C::PITCH * sizeof(cf);   // 16 x 264 = 4224
+    static constexpr int CHUNKS = C::K1L;                                       // 8
+    static constexpr unsigned STAGE_BYTES = CHUNKS * CHUNK_BYTES;               // 33 792
+    static_assert(CHUNK_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
+};
+
+__device__ __forceinline__ void bulk_push(unsigned dst_cluster, unsigned src_cta, unsigned bytes, unsigned bar_cluster) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(bar_cluster) : "memory");
+}
+
+template <class C, class MaskT, int MIN_CTAS, bool ACCUM>
+__global__ void __launch_bounds__(C::T, MIN_CTAS) fir_cluster2b_kernel(const FirKernelArgs a, const FirExtra ex) {
+    typedef Cluster2Layout<C> L;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cf* tile = reinterpret_cast<cf*>(smem_raw);
+    cf* stage = reinterpret_cast<cf*>(smem_raw + (size_t)C::TILE * sizeof(cf));
+    __shared__ __align__(8) unsigned long long bars[2];   // [0] full (tx count), [1] freed (CS arrivals)
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const unsigned rank = cluster_rank(), peer = rank ^ 1u;
+    const long long item = blockIdx.x / C::CS;
+    const FirItem<float> it = fir_item<float>(a, item);
+    const int tcol = t + (int)rank * C::MC;
+    const unsigned full_l = smem_u32(&bars[0]), freed_l = smem_u32(&bars[1]);
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full_l));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(freed_l), "r"((unsigned)C::CS));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_l), "r"(L::STAGE_BYTES) : "memory");
+    }
+    const unsigned peer_tile = map_to_rank(smem_u32(tile), peer), peer_full = map_to_rank(full_l, peer);
+    cf v[32];
+    load_window<C, IoF32>(v, tcol, it.xa, it.xb, it.ws, a.g.n_in);
+    if (rank == 0) fir_prefetch_l2<C::N, C::T, float>(a, item, t);
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+
+    // ---- forward stage 1: own sub-transforms go to the tile, the peer's to the staging buffer ----------------
+    static_for<0, C::B1>([&](auto U) {
+        constexpr int u = decltype(U)::value;
+        cf* b = v + u * C::N1;
+        dft<C::N1, -1>(b);
+        const int r = tcol + u * C::T;
+        apply_powers<C::N1, false, true>(b, tw1_at(a.tw1, r));
+        const int row0 = r >> 5;                       // global n2 row, in [rank*N2L, (rank+1)*N2L)
+        const int row0l = row0 - (int)rank * C::N2L;   // row inside a staging chunk
+        static_for<0, C::N1>([&](auto K) {
+            constexpr int k1 = decltype(K)::value;
+            constexpr int d = k1 / C::K1L, kl = k1 % C::K1L;
+            cf* dst = ((unsigned)d == rank) ? tile + (kl * C::N2 + row0) * C::PITCH + lane
+                                            : stage + (kl * L::CHUNK_ROWS + row0l) * C::PITCH + lane;
+            *dst = b[brev<C::N1>(k1)];
+        });
+    });
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes visible to the bulk-copy engine
+    __syncthreads();
+    if (t < L::CHUNKS)   // chunk t of the staging buffer = rows [t*N2 + rank*N2L, +N2L) of the peer's tile
+        bulk_push(peer_tile + (unsigned)((t * C::N2 + (int)rank * C::N2L) * C::PITCH * sizeof(cf)),
+                  smem_u32(stage) + (unsigned)t * L::CHUNK_BYTES, L::CHUNK_BYTES, peer_full);
+    mbar_wait(full_l, 0);                                  // the peer's half has landed in this tile
+    if (t == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_l), "r"(L::STAGE_BYTES) : "memory");
+    fwd_stage2<C>(v, t, a.tw2, tile);
+    __syncwarp();
+    mid_stage3<C, MaskT>(v, t, reinterpret_cast<const MaskT*>(a.mask) + (size_t)rank * 32 * C::T, tile);
+    __syncwarp();
+    cl_inv_stage2_load<C>(v, t, tile);
+    __syncthreads();                                       // this CTA's tile has been read completely
+    if (t < C::CS)
+        asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(map_to_rank(freed_l, (unsigned)t)) : "memory");
+    twiddle_idft<C::N2, C::B2>(v, a.tw2[lane]);
+    // The peer's arrival on `freed` also tells that it has consumed the forward push, i.e. that the bulk copies
+    // have finished reading this CTA's staging buffer: it may be refilled now.
+    mbar_wait(freed_l, 0);
+    // ---- inverse push: value (k1 = rank*K1L + warp, column n2*32 + lane) -> owner of the column ---------------
+    static_for<0, C::B2>([&](auto U) {
+        constexpr int u = decltype(U)::value;
+        const cf* b = v + u * C::N2;
+        const int kl = warp + u * C::WARPS;            // local sub-transform
+        const int k1 = (int)rank * C::K1L + kl;
+        static_for<0, C::N2>([&](auto K) {
+            constexpr int n2 = decltype(K)::value;
+            constexpr int d = (n2 * 32) / C::MC, rl = (n2 * 32) % C::MC;
+            cf* dst = ((unsigned)d == rank) ? tile + (k1 * C::N2L + (rl >> 5)) * C::PITCH + lane
+                                            : stage + (kl * L::CHUNK_ROWS + (rl >> 5)) * C::PITCH + lane;
+            *dst = b[brev<C::N2>(n2)];
+        });
+    });
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (t < L::CHUNKS)   // chunk t = rows [(rank*K1L + t)*N2L, +N2L) of the peer's tile (inverse stage-1 layout)
+        bulk_push(peer_tile + (unsigned)((((int)rank * C::K1L + t) * C::N2L) * C::PITCH * sizeof(cf)),
+                  smem_u32(stage) + (unsigned)t * L::CHUNK_BYTES, L::CHUNK_BYTES, peer_full);
     mbar_wait(full_l, 1);
     cl_inv_stage1<C>(v, t, tcol, a.tw1, tile);
     store_slice<C, IoF32, false, ACCUM>(v, tcol, it.ya, it.yb, it.m0, a.g, ex.shape);

@@ -13,4 +13,8 @@ const FirVariant* fir_variant_c2_16384() {
     static const FirVariant v = make_variant_cluster<FirClusterCfg<16, 32, 2>, 2>("c2");
     return &v;
 }
+const FirVariant* fir_variant_b2_16384() {
+    static const FirVariant v = make_variant_cluster2b<FirClusterCfg<16, 32, 2>, 2>("b2");
+    return &v;
+}
 }  // namespace adt

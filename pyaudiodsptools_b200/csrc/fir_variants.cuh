@@ -143,6 +143,17 @@ FirVariant make_variant_cluster(const char* name) {
     };
     return v;
 }
+// 2-CTA cluster with the bulk (TMA-engine) DSMEM exchange: tile + staging buffer per CTA
+template <class C, int MIN_CTAS>
+FirVariant make_variant_cluster2b(const char* name) {
+    FirVariant v = make_variant_cluster<C, MIN_CTAS>(name);
+    v.smem = (size_t)C::TILE * sizeof(cf) + Cluster2Layout<C>::STAGE_BYTES;
+    v.cplx = fir_cluster2b_kernel<C, cf, MIN_CTAS, false>;
+    v.real = fir_cluster2b_kernel<C, float, MIN_CTAS, false>;
+    v.accum_cplx = fir_cluster2b_kernel<C, cf, MIN_CTAS, true>;
+    v.accum_real = fir_cluster2b_kernel<C, float, MIN_CTAS, true>;
+    return v;
+}
 #endif
 #endif  // ADT_FIR_VARIANT_IMPL
 
@@ -154,5 +165,6 @@ const FirVariant* fir_variant_p16_4096();
 const FirVariant* fir_variant_p16_8192();
 const FirVariant* fir_variant_c4_32768();   // 4-CTA cluster, N = 32768
 const FirVariant* fir_variant_c2_16384();   // 2-CTA cluster, N = 16384 (A/B against the one-CTA kernel)
+const FirVariant* fir_variant_b2_16384();   // 2-CTA cluster, N = 16384, bulk DSMEM exchange through a staging buffer
 
 }  // namespace adt

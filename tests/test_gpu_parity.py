@@ -44,11 +44,12 @@ def test_whole_buffer_matches_reference(gpu_lib, name):
 
 
 @pytest.mark.parametrize("fft_size,kernel", [(4096, "p16"), (8192, "p16"), (4096, "p32"), (8192, "p32"), (16384, "p32"),
-                                             (16384, "c2"), (32768, "c4")])
+                                             (16384, "c2"), (16384, "b2"), (32768, "c4")])
 @pytest.mark.parametrize("name", ["highcut4000_c512_noise", "eq3fft_c512_noise", "lowcut160_default_c1024_noise"])
 def test_every_kernel_variant(gpu_lib, monkeypatch, name, fft_size, kernel):
     """p16 / p32 = 16 / 32 complex points per thread (fft_core16.cuh / fft_core.cuh), c2 / c4 = one transform on a
-    2- / 4-CTA thread-block cluster with the transposition through distributed shared memory (fir_cluster.cuh);
+    2- / 4-CTA thread-block cluster with the transposition through distributed shared memory (fir_cluster.cuh;
+    b2 = the 2-CTA cluster with the bulk-copy-engine exchange through a staging buffer);
     real and complex masks."""
     meta, arr = load_golden(name)
     if kernel == "p16" and b"ab_variants=1" not in gpu_lib.adt_version():
