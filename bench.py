@@ -262,10 +262,11 @@ class ClockSampler:
 # GPU arm
 # ---------------------------------------------------------------------------
 def _kernel_src_sha():
-    """Hash of the sources of the hot kernel: a committed ncu traffic figure is only quoted while it matches."""
+    """Hash of the sources of the hot kernel (arithmetic, kernel body, its instantiation parameters): a committed
+    ncu traffic figure is only quoted while it matches."""
     import hashlib
     h = hashlib.sha256()
-    for name in ("fft_core.cuh", "fir_kernel.cuh", "fir_variants.cuh", "fir_k8192.cu"):
+    for name in ("fft_core.cuh", "fir_kernel.cuh", "fir_k8192.cu"):
         with open(os.path.join(ROOT, "pyaudiodsptools_b200", "csrc", name), "rb") as f:
             h.update(f.read())
     return h.hexdigest()[:16]
