@@ -22,6 +22,9 @@
 
 #include "adt_internal.h"
 
+#ifndef ADT_BIQUAD_PIPE_DEFAULT
+#define ADT_BIQUAD_PIPE_DEFAULT 0   /* 1: helper + chain warp per band (biquad3p_kernel) */
+#endif
 #ifndef ADT_BIQUAD_ROUND_INT_DEFAULT
 #define ADT_BIQUAD_ROUND_INT_DEFAULT 0   /* set from the measurement in tools/microbench/lat64.cu */
 #endif
@@ -247,6 +250,120 @@ __global__ void __launch_bounds__(96) biquad3_kernel(const T* __restrict__ x, T*
     }
 }
 
+
+// ---- the chain with HELPER warps (biquad3p_kernel) ------------------------------------------------------------
+// A warp issues in order and is alone on its SM partition, so in biquad3_kernel every conversion or feed-forward
+// product the compiler places next to its consumer stalls the feedback chain: ~135 cycles per sample against
+// the 62 of the bare chain (tools/microbench/lat64.cu).  Here each band has TWO warps: a helper that turns a tile
+// of inputs into the feed-forward sums ff[j] = (c0*x[j-1] + c1*x[j-2]) + c2*x[j-3] — throughput-bound,
+// independent of the outputs — and a chain warp that only runs acc = (ff - c3*y1) - c4*y2, rounds and feeds
+// back.  Six warps form a pipeline over 32-sample tiles (helper of band b on tile s-2b, chain on tile s-2b-1);
+// tiles travel as float64 in double-buffered shared memory, one block barrier per step.  Same individually
+// rounded operations in the same order as biquad_kernel -> bit-identical.
+#define ADT_BQ3P_SMEM(T) (10 * 32 * 33 * sizeof(double) + 2 * 32 * 33 * sizeof(T))
+
+template <typename T>
+__global__ void __launch_bounds__(192) biquad3p_kernel(const T* __restrict__ x, T* __restrict__ y, long long pitch,
+                                                       long long n, int n_channels, Biquad3Args a) {
+    extern __shared__ __align__(16) unsigned char bq_smem[];
+    typedef double TileD[32][33];
+    typedef T TileT[32][33];
+    TileD* ffb = reinterpret_cast<TileD*>(bq_smem);            // [band*2 + parity] feed-forward sums
+    TileD* yb = ffb + 6;                                       // [band*2 + parity] band outputs (bands 0, 1)
+    TileT* io = reinterpret_cast<TileT*>(bq_smem + 10 * sizeof(TileD));   // [0] input transposition, [1] output
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int band = warp >> 1;
+    const bool is_chain = warp & 1;
+    const int c0 = blockIdx.x * 32;
+    const int ch = c0 + lane;
+    const bool live = ch < n_channels;
+    const int rows = min(32, n_channels - c0);
+    const BiquadCoef k = a.k[band];
+    double s0 = 0, s1 = 0, s2 = 0;     // helper: x[n-1], x[n-2], x[n-3];  chain: y[n-1], y[n-2]
+    if (live) {
+        const double* st = a.state[band] + (long long)ch * 5;
+        if (is_chain) { s0 = st[3]; s1 = st[4]; } else { s0 = st[0]; s1 = st[1]; s2 = st[2]; }
+    }
+    const long long n_tiles = (n + 31) / 32;
+    const T* xr = x + (long long)c0 * pitch + lane;
+    T* yr = y + (long long)c0 * pitch + lane;
+    T nxt[32];
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) nxt[i] = (i < rows && lane < n) ? xr[(long long)i * pitch] : T(0);
+    }
+    for (long long step = 0; step < n_tiles + 5; ++step) {
+        const long long tile = step - warp;                    // helper of band b: step - 2b, chain: step - 2b - 1
+        const bool active = tile >= 0 && tile < n_tiles;
+        const long long base = tile * 32;
+        const int w = active ? (int)min((long long)32, n - base) : 0;
+        const int par = (int)(tile & 1);
+        if (active && !is_chain) {
+            // ---- helper: inputs (global for band 0, the previous band's float64 outputs otherwise) -> ff ----
+            TileD& ff = ffb[band * 2 + par];
+            if (band == 0) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) io[0][i][lane] = nxt[i];
+                __syncwarp();
+                const long long nb = base + 32;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) nxt[i] = (i < rows && nb + lane < n) ? xr[(long long)i * pitch + nb] : T(0);
+            }
+            auto in_at = [&](int j) -> double { return band == 0 ? (double)io[0][lane][j] : yb[(band - 1) * 2 + par][lane][j]; };
+            if (w == 32) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const double xin = in_at(j);
+                    double f = __dmul_rn(k.c[0], s0);
+                    f = __dadd_rn(f, __dmul_rn(k.c[1], s1));
+                    ff[lane][j] = __dadd_rn(f, __dmul_rn(k.c[2], s2));
+                    s2 = s1; s1 = s0; s0 = xin;
+                }
+            } else {
+                for (int j = 0; j < w; ++j) {
+                    const double xin = in_at(j);
+                    double f = __dmul_rn(k.c[0], s0);
+                    f = __dadd_rn(f, __dmul_rn(k.c[1], s1));
+                    ff[lane][j] = __dadd_rn(f, __dmul_rn(k.c[2], s2));
+                    s2 = s1; s1 = s0; s0 = xin;
+                }
+            }
+        }
+        if (active && is_chain) {
+            // ---- chain: only the feedback recurrence ----
+            TileD& ff = ffb[band * 2 + par];
+            auto one = [&](int j) {
+                double acc = __dsub_rn(ff[lane][j], __dmul_rn(k.c[3], s0));
+                acc = __dsub_rn(acc, __dmul_rn(k.c[4], s1));
+                T out;
+                const double fb = BiquadRound<T, false>::run(acc, &out);
+                if (band == 2)
+                    io[1][lane][j] = out;
+                else
+                    yb[band * 2 + par][lane][j] = fb;
+                s1 = s0; s0 = fb;
+            };
+            if (w == 32) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) one(j);
+            } else {
+                for (int j = 0; j < w; ++j) one(j);
+            }
+            if (band == 2) {
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (i < rows && lane < w) yr[(long long)i * pitch + base] = io[1][i][lane];
+            }
+        }
+        __syncthreads();   // every tile moves one pipeline stage
+    }
+    if (live) {
+        double* st = a.state[band] + (long long)ch * 5;
+        if (is_chain) { st[3] = s0; st[4] = s1; } else { st[0] = s0; st[1] = s1; st[2] = s2; }
+    }
+}
+
 }  // namespace
 
 struct adt_biquad {
@@ -362,6 +479,26 @@ extern "C" int adt_biquad_chain_apply_dev(adt_biquad* low, adt_biquad* mid, adt_
         a.state[i] = b[i]->d_state;
     }
     const unsigned grid = (unsigned)((low->n_channels + 31) / 32);
+    static const int pipe = getenv("ADT_BIQUAD_PIPE") ? atoi(getenv("ADT_BIQUAD_PIPE")) : ADT_BIQUAD_PIPE_DEFAULT;
+    if (pipe) {   // helper + chain warp per band (biquad3p_kernel)
+        static bool attr_p = false;
+        if (!attr_p) {
+            ADT_CK(ctx, cudaFuncSetAttribute((const void*)biquad3p_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)ADT_BQ3P_SMEM(double)));
+            ADT_CK(ctx, cudaFuncSetAttribute((const void*)biquad3p_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)ADT_BQ3P_SMEM(float)));
+            attr_p = true;
+        }
+        if (low->f64)
+            biquad3p_kernel<double><<<grid, 192, ADT_BQ3P_SMEM(double), ctx->stream>>>((const double*)x, (double*)y, pitch, n,
+                                                                                      low->n_channels, a);
+        else
+            biquad3p_kernel<float><<<grid, 192, ADT_BQ3P_SMEM(float), ctx->stream>>>((const float*)x, (float*)y, pitch, n,
+                                                                                    low->n_channels, a);
+        ADT_CK(ctx, cudaGetLastError());
+        ctx->launches++;
+        return ADT_OK;
+    }
     static const int round_int = getenv("ADT_BIQUAD_ROUND_INT") ? atoi(getenv("ADT_BIQUAD_ROUND_INT")) : ADT_BIQUAD_ROUND_INT_DEFAULT;
     if (low->f64) {
         const size_t smem = 6 * 32 * 33 * sizeof(double);
