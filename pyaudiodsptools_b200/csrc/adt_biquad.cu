@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(96) biquad3_kernel(const T* __restrict__ x, T*
 // back.  Six warps form a pipeline over 32-sample tiles (helper of band b on tile s-2b, chain on tile s-2b-1);
 // tiles travel as float64 in double-buffered shared memory, one block barrier per step.  Same individually
 // rounded operations in the same order as biquad_kernel -> bit-identical.
-#define ADT_BQ3P_SMEM(T) (10 * 32 * 33 * sizeof(double) + 2 * 32 * 33 * sizeof(T))
+#define ADT_BQ3P_SMEM(T) (11 * 32 * 33 * sizeof(double) + 32 * 33 * sizeof(T))
 
 template <typename T>
 __global__ void __launch_bounds__(192) biquad3p_kernel(const T* __restrict__ x, T* __restrict__ y, long long pitch,
@@ -270,7 +270,8 @@ __global__ void __launch_bounds__(192) biquad3p_kernel(const T* __restrict__ x, 
     typedef T TileT[32][33];
     TileD* ffb = reinterpret_cast<TileD*>(bq_smem);            // [band*2 + parity] feed-forward sums
     TileD* yb = ffb + 6;                                       // [band*2 + parity] band outputs (bands 0, 1)
-    TileT* io = reinterpret_cast<TileT*>(bq_smem + 10 * sizeof(TileD));   // [0] input transposition, [1] output
+    TileD& xin_t = ffb[10];                                    // input tile, converted to float64 while it is transposed
+    TileT& out_t = *reinterpret_cast<TileT*>(bq_smem + 11 * sizeof(TileD));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int band = warp >> 1;
     const bool is_chain = warp & 1;
@@ -303,21 +304,25 @@ __global__ void __launch_bounds__(192) biquad3p_kernel(const T* __restrict__ x, 
             TileD& ff = ffb[band * 2 + par];
             if (band == 0) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) io[0][i][lane] = nxt[i];
+                for (int i = 0; i < 32; ++i) xin_t[i][lane] = (double)nxt[i];   // 32 independent conversions: they pipeline
                 __syncwarp();
                 const long long nb = base + 32;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) nxt[i] = (i < rows && nb + lane < n) ? xr[(long long)i * pitch + nb] : T(0);
             }
-            auto in_at = [&](int j) -> double { return band == 0 ? (double)io[0][lane][j] : yb[(band - 1) * 2 + par][lane][j]; };
+            const TileD& src = band == 0 ? xin_t : yb[(band - 1) * 2 + par];
+            auto in_at = [&](int j) -> double { return src[lane][j]; };
             if (w == 32) {
+                double xi[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) xi[j] = in_at(j);
+                asm volatile("" ::: "memory");
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const double xin = in_at(j);
                     double f = __dmul_rn(k.c[0], s0);
                     f = __dadd_rn(f, __dmul_rn(k.c[1], s1));
                     ff[lane][j] = __dadd_rn(f, __dmul_rn(k.c[2], s2));
-                    s2 = s1; s1 = s0; s0 = xin;
+                    s2 = s1; s1 = s0; s0 = xi[j];
                 }
             } else {
                 for (int j = 0; j < w; ++j) {
@@ -338,14 +343,30 @@ __global__ void __launch_bounds__(192) biquad3p_kernel(const T* __restrict__ x, 
                 T out;
                 const double fb = BiquadRound<T, false>::run(acc, &out);
                 if (band == 2)
-                    io[1][lane][j] = out;
+                    out_t[lane][j] = out;
                 else
                     yb[band * 2 + par][lane][j] = fb;
                 s1 = s0; s0 = fb;
             };
             if (w == 32) {
+                // all 32 operands into registers first (the compiler otherwise issues each LDS right before its
+                // consumer, and the in-order warp then waits a shared-memory latency per sample on top of the chain)
+                double f[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) one(j);
+                for (int j = 0; j < 32; ++j) f[j] = ff[lane][j];
+                asm volatile("" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    double acc = __dsub_rn(f[j], __dmul_rn(k.c[3], s0));
+                    acc = __dsub_rn(acc, __dmul_rn(k.c[4], s1));
+                    T out;
+                    const double fb = BiquadRound<T, false>::run(acc, &out);
+                    if (band == 2)
+                        out_t[lane][j] = out;
+                    else
+                        yb[band * 2 + par][lane][j] = fb;
+                    s1 = s0; s0 = fb;
+                }
             } else {
                 for (int j = 0; j < w; ++j) one(j);
             }
@@ -353,7 +374,7 @@ __global__ void __launch_bounds__(192) biquad3p_kernel(const T* __restrict__ x, 
                 __syncwarp();
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
-                    if (i < rows && lane < w) yr[(long long)i * pitch + base] = io[1][i][lane];
+                    if (i < rows && lane < w) yr[(long long)i * pitch + base] = out_t[i][lane];
             }
         }
         __syncthreads();   // every tile moves one pipeline stage
