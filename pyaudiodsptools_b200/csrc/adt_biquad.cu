@@ -42,6 +42,33 @@ __device__ __forceinline__ float round_to<float>(double v) { return __double2flo
 template <>
 __device__ __forceinline__ double round_to<double>(double v) { return v; }
 
+// ---- input tiles through an asynchronous ring -------------------------------------------------------------------
+// Measured (tools/biquad_clock_probe.py, both chain kernels at 32.9 ms to within 0.2 %): the recurrence kernels
+// were bound by the LATENCY of the one-tile-ahead global loads — 32 rows in 32 different 2 MB pages per tile,
+// ~2.4 us per round trip — not by arithmetic.  The loader warp therefore keeps BQ_RING - 1 tiles in flight with
+// cp.async (LDGSTS: global -> shared without registers); rows beyond the channel count and samples beyond n are
+// zero-filled by the copy itself (src-size 0).
+#define BQ_RING 8
+template <int BYTES>
+__device__ __forceinline__ void bq_cp_async(void* dst_smem, const void* src, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(d), "l"(src), "n"(BYTES), "r"(valid ? BYTES : 0) : "memory");
+}
+// tile `tile` (32 samples x 32 channels) -> slot[tile % BQ_RING][channel][sample]; always commits one group
+template <typename T>
+__device__ __forceinline__ void bq_issue_tile(T (*slot)[32][33], long long tile, const T* x, long long row0, long long pitch,
+                                              long long n, int rows, int lane) {
+    T (&dst)[32][33] = slot[tile % BQ_RING];
+    const long long smp = tile * 32 + lane;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const bool ok = i < rows && smp < n;
+        bq_cp_async<sizeof(T)>(&dst[i][lane], ok ? x + (row0 + i) * pitch + smp : x, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bq_wait_tile() { asm volatile("cp.async.wait_group %0;" ::"n"(BQ_RING - 1) : "memory"); }
+
 // state: [n_channels][5] doubles = x[n-1], x[n-2], x[n-3], y[n-1], y[n-2]
 // One warp per CTA (32 channels); the global loads of tile k+1 are issued into registers before tile k is
 // filtered, so HBM latency hides behind the fp64 recurrence (the real bound: ~40 dependent cycles/sample).
@@ -49,7 +76,10 @@ template <typename T>
 __global__ void __launch_bounds__(32) biquad_kernel(const T* __restrict__ x, T* __restrict__ y, long long pitch,
                                                     long long n, int n_channels, BiquadCoef k,
                                                     double* __restrict__ state) {
-    __shared__ T tl[32][33];
+    extern __shared__ __align__(16) unsigned char bq_smem[];
+    typedef T Tile[32][33];
+    Tile* ring = reinterpret_cast<Tile*>(bq_smem);             // BQ_RING input tiles
+    Tile& tl = ring[BQ_RING];                                  // output tile
     const int lane = threadIdx.x;
     const int c0 = blockIdx.x * 32;
     if (c0 >= n_channels) return;
@@ -61,24 +91,19 @@ __global__ void __launch_bounds__(32) biquad_kernel(const T* __restrict__ x, T* 
         x1 = s[0]; x2 = s[1]; x3 = s[2]; y1 = s[3]; y2 = s[4];
     }
     const int rows = min(32, n_channels - c0);
-    const T* xr = x + (long long)c0 * pitch + lane;
     T* yr = y + (long long)c0 * pitch + lane;
-    T nxt[32];
-    // prologue: tile 0 into registers (row i of the tile = 32 consecutive samples of channel c0 + i)
-#pragma unroll
-    for (int i = 0; i < 32; ++i) nxt[i] = (i < rows && lane < n) ? xr[(long long)i * pitch] : T(0);
-    for (long long base = 0; base < n; base += 32) {
+    const long long n_tiles = (n + 31) / 32;
+    for (int p = 0; p < BQ_RING - 1; ++p) bq_issue_tile<T>(ring, p, x, c0, pitch, n, rows, lane);
+    for (long long tile = 0; tile < n_tiles; ++tile) {
+        const long long base = tile * 32;
         const int w = (int)min((long long)32, n - base);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) tl[i][lane] = nxt[i];
+        bq_issue_tile<T>(ring, tile + BQ_RING - 1, x, c0, pitch, n, rows, lane);
+        bq_wait_tile();
         __syncwarp();
-        // prefetch the next tile while this one is filtered
-        const long long nb = base + 32;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) nxt[i] = (i < rows && nb + lane < n) ? xr[(long long)i * pitch + nb] : T(0);
+        Tile& src = ring[tile % BQ_RING];
         if (live) {
             for (int j = 0; j < w; ++j) {
-                const double xin = (double)tl[lane][j];
+                const double xin = (double)src[lane][j];
                 // ((((c0*x1) + (c1*x2)) + (c2*x3)) - (c3*y1)) - (c4*y2), EffectEQ3Band.py:112
                 double acc = __dmul_rn(k.c[0], x1);
                 acc = __dadd_rn(acc, __dmul_rn(k.c[1], x2));
@@ -97,11 +122,13 @@ __global__ void __launch_bounds__(32) biquad_kernel(const T* __restrict__ x, T* 
             if (i < rows && lane < w) yr[(long long)i * pitch + base] = tl[i][lane];
         __syncwarp();
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (live) {
         double* s = state + (long long)ch * 5;
         s[0] = x1; s[1] = x2; s[2] = x3; s[3] = y1; s[4] = y2;
     }
 }
+#define ADT_BQ1_SMEM(T) ((BQ_RING + 1) * 32 * 33 * sizeof(T))
 
 
 // ---- low -> mid -> high chain in ONE launch -----------------------------------------------------------
@@ -157,7 +184,8 @@ __global__ void __launch_bounds__(96) biquad3_kernel(const T* __restrict__ x, T*
                                                      long long n, int n_channels, Biquad3Args a) {
     extern __shared__ __align__(16) unsigned char bq_smem[];
     typedef T Tile[32][33];
-    Tile* tiles = reinterpret_cast<Tile*>(bq_smem);   // [0] input, [1..2] low->mid, [3..4] mid->high, [5] output
+    Tile* tiles = reinterpret_cast<Tile*>(bq_smem);   // [1..2] low->mid, [3..4] mid->high, [5] output ([0] unused)
+    Tile* ring = tiles + 6;                           // BQ_RING input tiles filled by cp.async (band 0's warp)
     const int lane = threadIdx.x & 31, band = threadIdx.x >> 5;
     const int c0 = blockIdx.x * 32;
     const int ch = c0 + lane;
@@ -170,27 +198,20 @@ __global__ void __launch_bounds__(96) biquad3_kernel(const T* __restrict__ x, T*
         x1 = s[0]; x2 = s[1]; x3 = s[2]; y1 = s[3]; y2 = s[4];
     }
     const long long n_tiles = (n + 31) / 32;
-    const T* xr = x + (long long)c0 * pitch + lane;
     T* yr = y + (long long)c0 * pitch + lane;
-    T nxt[32];
-    if (band == 0) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) nxt[i] = (i < rows && lane < n) ? xr[(long long)i * pitch] : T(0);
-    }
+    if (band == 0)
+        for (int p = 0; p < BQ_RING - 1; ++p) bq_issue_tile<T>(ring, p, x, c0, pitch, n, rows, lane);
     for (long long step = 0; step < n_tiles + 2; ++step) {
         const long long tile = step - band;
         const bool active = tile >= 0 && tile < n_tiles;
         const long long base = tile * 32;
         const int w = active ? (int)min((long long)32, n - base) : 0;
-        Tile& src = band == 0 ? tiles[0] : tiles[(band == 1 ? 1 : 3) + (int)(tile & 1)];
+        Tile& src = band == 0 ? ring[(active ? tile : 0) % BQ_RING] : tiles[(band == 1 ? 1 : 3) + (int)(tile & 1)];
         Tile& dst = band == 2 ? tiles[5] : tiles[(band == 0 ? 1 : 3) + (int)(tile & 1)];
         if (band == 0 && active) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) src[i][lane] = nxt[i];
+            bq_issue_tile<T>(ring, tile + BQ_RING - 1, x, c0, pitch, n, rows, lane);   // keep BQ_RING - 1 tiles in flight
+            bq_wait_tile();                                                            // this step's tile has landed
             __syncwarp();
-            const long long nb = base + 32;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) nxt[i] = (i < rows && nb + lane < n) ? xr[(long long)i * pitch + nb] : T(0);
         }
         if (active && live) {
             // Full tiles run a fixed 32-iteration loop, unrolled so that the loads, the float -> double
@@ -244,11 +265,14 @@ __global__ void __launch_bounds__(96) biquad3_kernel(const T* __restrict__ x, T*
         }
         __syncthreads();   // hand the tiles over: band b's output of this step is band b+1's input of the next
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (live) {
         double* s = a.state[band] + (long long)ch * 5;
         s[0] = x1; s[1] = x2; s[2] = x3; s[3] = y1; s[4] = y2;
     }
 }
+#define ADT_BQ3_SMEM(T) ((6 + BQ_RING) * 32 * 33 * sizeof(T))
+
 
 
 // ---- the chain with HELPER warps (biquad3p_kernel) ------------------------------------------------------------
@@ -260,7 +284,7 @@ __global__ void __launch_bounds__(96) biquad3_kernel(const T* __restrict__ x, T*
 // back.  Six warps form a pipeline over 32-sample tiles (helper of band b on tile s-2b, chain on tile s-2b-1);
 // tiles travel as float64 in double-buffered shared memory, one block barrier per step.  Same individually
 // rounded operations in the same order as biquad_kernel -> bit-identical.
-#define ADT_BQ3P_SMEM(T) (11 * 32 * 33 * sizeof(double) + 32 * 33 * sizeof(T))
+#define ADT_BQ3P_SMEM(T) (10 * 32 * 33 * sizeof(double) + (1 + BQ_RING) * 32 * 33 * sizeof(T))
 
 template <typename T>
 __global__ void __launch_bounds__(192) biquad3p_kernel(const T* __restrict__ x, T* __restrict__ y, long long pitch,
@@ -270,8 +294,8 @@ __global__ void __launch_bounds__(192) biquad3p_kernel(const T* __restrict__ x, 
     typedef T TileT[32][33];
     TileD* ffb = reinterpret_cast<TileD*>(bq_smem);            // [band*2 + parity] feed-forward sums
     TileD* yb = ffb + 6;                                       // [band*2 + parity] band outputs (bands 0, 1)
-    TileD& xin_t = ffb[10];                                    // input tile, converted to float64 while it is transposed
-    TileT& out_t = *reinterpret_cast<TileT*>(bq_smem + 11 * sizeof(TileD));
+    TileT& out_t = *reinterpret_cast<TileT*>(bq_smem + 10 * sizeof(TileD));
+    TileT* ring = &out_t + 1;                                  // BQ_RING input tiles filled by cp.async (warp 0)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int band = warp >> 1;
     const bool is_chain = warp & 1;
@@ -286,13 +310,9 @@ __global__ void __launch_bounds__(192) biquad3p_kernel(const T* __restrict__ x, 
         if (is_chain) { s0 = st[3]; s1 = st[4]; } else { s0 = st[0]; s1 = st[1]; s2 = st[2]; }
     }
     const long long n_tiles = (n + 31) / 32;
-    const T* xr = x + (long long)c0 * pitch + lane;
     T* yr = y + (long long)c0 * pitch + lane;
-    T nxt[32];
-    if (warp == 0) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) nxt[i] = (i < rows && lane < n) ? xr[(long long)i * pitch] : T(0);
-    }
+    if (warp == 0)
+        for (int p = 0; p < BQ_RING - 1; ++p) bq_issue_tile<T>(ring, p, x, c0, pitch, n, rows, lane);
     for (long long step = 0; step < n_tiles + 5; ++step) {
         const long long tile = step - warp;                    // helper of band b: step - 2b, chain: step - 2b - 1
         const bool active = tile >= 0 && tile < n_tiles;
@@ -303,15 +323,13 @@ __global__ void __launch_bounds__(192) biquad3p_kernel(const T* __restrict__ x, 
             // ---- helper: inputs (global for band 0, the previous band's float64 outputs otherwise) -> ff ----
             TileD& ff = ffb[band * 2 + par];
             if (band == 0) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) xin_t[i][lane] = (double)nxt[i];   // 32 independent conversions: they pipeline
+                bq_issue_tile<T>(ring, tile + BQ_RING - 1, x, c0, pitch, n, rows, lane);
+                bq_wait_tile();
                 __syncwarp();
-                const long long nb = base + 32;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) nxt[i] = (i < rows && nb + lane < n) ? xr[(long long)i * pitch + nb] : T(0);
             }
-            const TileD& src = band == 0 ? xin_t : yb[(band - 1) * 2 + par];
-            auto in_at = [&](int j) -> double { return src[lane][j]; };
+            const TileT& in0 = ring[tile % BQ_RING];
+            const TileD& inb = yb[(band > 0 ? band - 1 : 0) * 2 + par];
+            auto in_at = [&](int j) -> double { return band == 0 ? (double)in0[lane][j] : inb[lane][j]; };
             if (w == 32) {
                 double xi[32];
 #pragma unroll
@@ -379,6 +397,7 @@ __global__ void __launch_bounds__(192) biquad3p_kernel(const T* __restrict__ x, 
         }
         __syncthreads();   // every tile moves one pipeline stage
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (live) {
         double* st = a.state[band] + (long long)ch * 5;
         if (is_chain) { st[3] = s0; st[4] = s1; } else { st[0] = s0; st[1] = s1; st[2] = s2; }
@@ -444,11 +463,19 @@ extern "C" int adt_biquad_apply_dev(adt_biquad* b, const void* x, void* y, int64
     if (n == 0) return ADT_OK;
     ADT_CK(ctx, cudaSetDevice(ctx->device));
     const unsigned grid = (unsigned)((b->n_channels + 31) / 32);
+    static bool attr1 = false;
+    if (!attr1) {   // the double ring is 76 KB: dynamic shared memory above 48 KB is opt-in
+        ADT_CK(ctx, cudaFuncSetAttribute((const void*)biquad_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)ADT_BQ1_SMEM(double)));
+        ADT_CK(ctx, cudaFuncSetAttribute((const void*)biquad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)ADT_BQ1_SMEM(float)));
+        attr1 = true;
+    }
     if (b->f64)
-        biquad_kernel<double><<<grid, 32, 0, ctx->stream>>>((const double*)x, (double*)y, pitch, n, b->n_channels, b->k,
+        biquad_kernel<double><<<grid, 32, ADT_BQ1_SMEM(double), ctx->stream>>>((const double*)x, (double*)y, pitch, n, b->n_channels, b->k,
                                                              b->d_state);
     else
-        biquad_kernel<float><<<grid, 32, 0, ctx->stream>>>((const float*)x, (float*)y, pitch, n, b->n_channels, b->k,
+        biquad_kernel<float><<<grid, 32, ADT_BQ1_SMEM(float), ctx->stream>>>((const float*)x, (float*)y, pitch, n, b->n_channels, b->k,
                                                             b->d_state);
     ADT_CK(ctx, cudaGetLastError());
     ctx->launches++;
@@ -521,25 +548,25 @@ extern "C" int adt_biquad_chain_apply_dev(adt_biquad* low, adt_biquad* mid, adt_
         return ADT_OK;
     }
     static const int round_int = getenv("ADT_BIQUAD_ROUND_INT") ? atoi(getenv("ADT_BIQUAD_ROUND_INT")) : ADT_BIQUAD_ROUND_INT_DEFAULT;
-    if (low->f64) {
-        const size_t smem = 6 * 32 * 33 * sizeof(double);
-        static bool attr_done = false;
-        if (!attr_done) {
-            ADT_CK(ctx, cudaFuncSetAttribute((const void*)biquad3_kernel<double, false>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_done = true;
-        }
-        biquad3_kernel<double, false><<<grid, 96, smem, ctx->stream>>>((const double*)x, (double*)y, pitch, n,
-                                                                      low->n_channels, a);
-    } else {
-        const size_t smem = 6 * 32 * 33 * sizeof(float);
-        if (round_int)
-            biquad3_kernel<float, true><<<grid, 96, smem, ctx->stream>>>((const float*)x, (float*)y, pitch, n,
-                                                                        low->n_channels, a);
-        else
-            biquad3_kernel<float, false><<<grid, 96, smem, ctx->stream>>>((const float*)x, (float*)y, pitch, n,
-                                                                         low->n_channels, a);
+    static bool attr_done = false;
+    if (!attr_done) {
+        ADT_CK(ctx, cudaFuncSetAttribute((const void*)biquad3_kernel<double, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ADT_BQ3_SMEM(double)));
+        ADT_CK(ctx, cudaFuncSetAttribute((const void*)biquad3_kernel<float, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ADT_BQ3_SMEM(float)));
+        ADT_CK(ctx, cudaFuncSetAttribute((const void*)biquad3_kernel<float, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ADT_BQ3_SMEM(float)));
+        attr_done = true;
     }
+    if (low->f64)
+        biquad3_kernel<double, false><<<grid, 96, ADT_BQ3_SMEM(double), ctx->stream>>>((const double*)x, (double*)y, pitch, n,
+                                                                                      low->n_channels, a);
+    else if (round_int)
+        biquad3_kernel<float, true><<<grid, 96, ADT_BQ3_SMEM(float), ctx->stream>>>((const float*)x, (float*)y, pitch, n,
+                                                                                   low->n_channels, a);
+    else
+        biquad3_kernel<float, false><<<grid, 96, ADT_BQ3_SMEM(float), ctx->stream>>>((const float*)x, (float*)y, pitch, n,
+                                                                                    low->n_channels, a);
     ADT_CK(ctx, cudaGetLastError());
     ctx->launches++;
     return ADT_OK;
