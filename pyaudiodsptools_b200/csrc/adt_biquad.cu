@@ -404,140 +404,6 @@ __global__ void __launch_bounds__(192) biquad3p_kernel(const T* __restrict__ x, 
     }
 }
 
-
-// ---- the helper/chain pipeline with QUEUES instead of a block barrier per tile (biquad3q_kernel) ---------------
-// Instrumenting biquad3p_kernel (clock64 per warp): the slowest stage works 77 cycles per sample, yet a step costs
-// 114 — the rest is the block barrier after every 32-sample tile, which makes each step as slow as whichever of
-// the six warps was slowest in it (memory-latency jitter of the loader, scheduling noise).  Here the six stages
-//   H0 -> C0 -> H1 -> C1 -> H2 -> C2       (H = feed-forward helper, C = feedback chain, per band)
-// run free: neighbours are coupled only by a BQ_Q-deep queue of float64 tiles in shared memory with one
-// "full" and one "empty" mbarrier per slot (producer: wait empty, fill, arrive full; consumer: wait full, drain,
-// arrive empty).  Jitter is absorbed by the queue, so throughput follows the slowest stage's AVERAGE.
-#define BQ_Q 3
-#define ADT_BQ3Q_SMEM(T) (5 * BQ_Q * 32 * 33 * sizeof(double) + (1 + BQ_RING) * 32 * 33 * sizeof(T))
-
-__device__ __forceinline__ void bq_mbar_init(unsigned long long* b) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(b)));
-}
-__device__ __forceinline__ void bq_mbar_arrive(unsigned long long* b) {
-    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
-}
-__device__ __forceinline__ void bq_mbar_wait(unsigned long long* b, unsigned parity) {
-    const unsigned addr = (unsigned)__cvta_generic_to_shared(b);
-    unsigned done = 0;
-    while (!done) {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n"
-                     "selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(192) biquad3q_kernel(const T* __restrict__ x, T* __restrict__ y, long long pitch,
-                                                       long long n, int n_channels, Biquad3Args a) {
-    extern __shared__ __align__(16) unsigned char bq_smem[];
-    typedef double TileD[32][33];
-    typedef T TileT[32][33];
-    TileD* queue = reinterpret_cast<TileD*>(bq_smem);          // [q * BQ_Q + slot], q = producer stage 0..4
-    TileT& out_t = *reinterpret_cast<TileT*>(bq_smem + 5 * BQ_Q * sizeof(TileD));
-    TileT* ring = &out_t + 1;                                  // BQ_RING input tiles filled by cp.async (stage 0)
-    __shared__ __align__(8) unsigned long long full_b[5 * BQ_Q], empty_b[5 * BQ_Q];
-    const int lane = threadIdx.x & 31, stage = threadIdx.x >> 5;
-    const int band = stage >> 1;
-    const bool is_chain = stage & 1;
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < 5 * BQ_Q; ++i) { bq_mbar_init(&full_b[i]); bq_mbar_init(&empty_b[i]); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const int c0 = blockIdx.x * 32;
-    const int ch = c0 + lane;
-    const bool live = ch < n_channels;
-    const int rows = min(32, n_channels - c0);
-    const BiquadCoef k = a.k[band];
-    double s0 = 0, s1 = 0, s2 = 0;     // helper: x[n-1], x[n-2], x[n-3];  chain: y[n-1], y[n-2]
-    if (live) {
-        const double* st = a.state[band] + (long long)ch * 5;
-        if (is_chain) { s0 = st[3]; s1 = st[4]; } else { s0 = st[0]; s1 = st[1]; s2 = st[2]; }
-    }
-    const long long n_tiles = (n + 31) / 32;
-    T* yr = y + (long long)c0 * pitch + lane;
-    if (stage == 0)
-        for (int p = 0; p < BQ_RING - 1; ++p) bq_issue_tile<T>(ring, p, x, c0, pitch, n, rows, lane);
-    for (long long tile = 0; tile < n_tiles; ++tile) {
-        const int slot = (int)(tile % BQ_Q);
-        const unsigned par = (unsigned)((tile / BQ_Q) & 1);
-        const int w = (int)min((long long)32, n - tile * 32);
-        // ---- operands of this tile into registers ----
-        double v[32];
-        if (stage == 0) {
-            bq_issue_tile<T>(ring, tile + BQ_RING - 1, x, c0, pitch, n, rows, lane);
-            bq_wait_tile();
-            __syncwarp();
-            const TileT& in0 = ring[tile % BQ_RING];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = (double)in0[lane][j];
-        } else {
-            const int qi = (stage - 1) * BQ_Q + slot;
-            bq_mbar_wait(&full_b[qi], par);
-            const TileD& in = queue[qi];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = in[lane][j];
-            __syncwarp();                                  // every lane has its operands: the slot may be refilled
-            if (lane == 0) bq_mbar_arrive(&empty_b[qi]);
-        }
-        asm volatile("" ::: "memory");
-        // ---- the stage's arithmetic, in place in v (samples beyond w are never used: w < 32 only on the last tile)
-        if (!is_chain) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                if (j < w) {
-                    double f = __dmul_rn(k.c[0], s0);
-                    f = __dadd_rn(f, __dmul_rn(k.c[1], s1));
-                    f = __dadd_rn(f, __dmul_rn(k.c[2], s2));
-                    s2 = s1; s1 = s0; s0 = v[j];
-                    v[j] = f;
-                }
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                if (j < w) {
-                    double acc = __dsub_rn(v[j], __dmul_rn(k.c[3], s0));
-                    acc = __dsub_rn(acc, __dmul_rn(k.c[4], s1));
-                    T out;
-                    const double fb = BiquadRound<T, false>::run(acc, &out);
-                    s1 = s0; s0 = fb;
-                    v[j] = fb;
-                }
-            }
-        }
-        // ---- results to the next stage (or to global memory after the last one) ----
-        if (stage < 5) {
-            const int qo = stage * BQ_Q + slot;
-            bq_mbar_wait(&empty_b[qo], par ^ 1u);          // passes at once the first time round
-            TileD& o = queue[qo];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) o[lane][j] = v[j];
-            __syncwarp();
-            if (lane == 0) bq_mbar_arrive(&full_b[qo]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) out_t[lane][j] = (T)v[j];   // exact: v[j] is the float64 image of the output
-            __syncwarp();
-            const long long base = tile * 32;
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-                if (i < rows && lane < w) yr[(long long)i * pitch + base] = out_t[i][lane];
-            __syncwarp();
-        }
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    if (live) {
-        double* st = a.state[band] + (long long)ch * 5;
-        if (is_chain) { st[3] = s0; st[4] = s1; } else { st[0] = s0; st[1] = s1; st[2] = s2; }
-    }
-}
-
 }  // namespace
 
 struct adt_biquad {
@@ -662,25 +528,6 @@ extern "C" int adt_biquad_chain_apply_dev(adt_biquad* low, adt_biquad* mid, adt_
     }
     const unsigned grid = (unsigned)((low->n_channels + 31) / 32);
     static const int pipe = getenv("ADT_BIQUAD_PIPE") ? atoi(getenv("ADT_BIQUAD_PIPE")) : ADT_BIQUAD_PIPE_DEFAULT;
-    if (pipe == 2) {   // helper + chain warp per band, stages coupled by queues (biquad3q_kernel)
-        static bool attr_q = false;
-        if (!attr_q) {
-            ADT_CK(ctx, cudaFuncSetAttribute((const void*)biquad3q_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)ADT_BQ3Q_SMEM(double)));
-            ADT_CK(ctx, cudaFuncSetAttribute((const void*)biquad3q_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)ADT_BQ3Q_SMEM(float)));
-            attr_q = true;
-        }
-        if (low->f64)
-            biquad3q_kernel<double><<<grid, 192, ADT_BQ3Q_SMEM(double), ctx->stream>>>((const double*)x, (double*)y, pitch, n,
-                                                                                      low->n_channels, a);
-        else
-            biquad3q_kernel<float><<<grid, 192, ADT_BQ3Q_SMEM(float), ctx->stream>>>((const float*)x, (float*)y, pitch, n,
-                                                                                    low->n_channels, a);
-        ADT_CK(ctx, cudaGetLastError());
-        ctx->launches++;
-        return ADT_OK;
-    }
     if (pipe) {   // helper + chain warp per band (biquad3p_kernel)
         static bool attr_p = false;
         if (!attr_p) {
