@@ -23,7 +23,7 @@
 #include "adt_internal.h"
 
 #ifndef ADT_BIQUAD_PIPE_DEFAULT
-#define ADT_BIQUAD_PIPE_DEFAULT 0   /* 1: helper + chain warp per band (biquad3p_kernel) */
+#define ADT_BIQUAD_PIPE_DEFAULT 1   /* 1: helper + chain warp per band (biquad3p_kernel, 27.4 ms); 0: one warp per band (biquad3_kernel, 31.7 ms) */
 #endif
 #ifndef ADT_BIQUAD_ROUND_INT_DEFAULT
 #define ADT_BIQUAD_ROUND_INT_DEFAULT 0   /* set from the measurement in tools/microbench/lat64.cu */
