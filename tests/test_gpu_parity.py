@@ -390,9 +390,10 @@ def test_biquad_batched_channels(gpu_lib):
         np.testing.assert_array_equal(y[ch], want)
 
 
-@pytest.mark.parametrize("round_int", ["0", "1"])
-def test_biquad_fused_chain_equals_three_launches(gpu_lib, round_int, tmp_path):
-    """The one-launch low->mid->high pipeline is bit-identical to the three per-band launches (and to the
+@pytest.mark.parametrize("pipe,round_int", [("1", "0"), ("0", "0"), ("0", "1")])
+def test_biquad_fused_chain_equals_three_launches(gpu_lib, pipe, round_int, tmp_path):
+    """The one-launch low->mid->high pipeline — helper + chain warp per band (pipe 1, the default) or one warp per
+    band (pipe 0) — is bit-identical to the three per-band launches (and to the
     oracle), shares their state, handles ragged tiles / channel counts, both rounding implementations, and
     float32 denormals (a decaying tail crosses 2^-126, where the integer rounding hands over to F2F)."""
     import os, subprocess, sys
@@ -428,5 +429,5 @@ assert np.array_equal(d.apply(xd)[2], od.applyhighband(od.applymidband(od.applyl
 print("fused chain ok")
 """)
     r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600,
-                       env=dict(os.environ, ADT_BIQUAD_ROUND_INT=round_int))
+                       env=dict(os.environ, ADT_BIQUAD_ROUND_INT=round_int, ADT_BIQUAD_PIPE=pipe))
     assert r.returncode == 0 and "fused chain ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
