@@ -132,8 +132,6 @@ __global__ void __launch_bounds__(2 * C::T, 1) fir_pingpong_kernel(const FirKern
     long long item = 2LL * blockIdx.x + pp.g;
     // Both groups run the token protocol in lock-step for the same number of rounds even when one of them has
     // run out of items (it then skips the work but still passes the token), so nobody waits for a token forever.
-    const long long per_cta = (a.n_items + 2LL * gridDim.x - 1) / (2LL * gridDim.x);   // upper bound of rounds, see below
-    (void)per_cta;
     if (pp.g == 1) pp.release();   // prime: group 0 owns the token first
     bool more = true;
     while (more) {
