@@ -148,6 +148,12 @@ extern "C" int adt_ctx_create(int device, adt_ctx** out) {
                 return ADT_ERR_CUDA;
             }
         }
+        if (v->smask_real &&   // tile + real mask table
+            cudaFuncSetAttribute((const void*)v->smask_real, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(v->smem + (size_t)v->n * sizeof(float))) != cudaSuccess) {
+            delete ctx;
+            return ADT_ERR_CUDA;
+        }
         for (fir_kernel_fn f : {v->pp_cplx, v->pp_real}) {   // two groups, two tiles per CTA
             if (!f) continue;
             if (cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * v->smem)) != cudaSuccess) {
@@ -471,6 +477,13 @@ static int fir_launch_seg(adt_fir* f, FirSeg& sg, bool accum, cudaStream_t s, co
         ctx->launches++;
         ex.work_counter = f->d_counter + slot;
         kpp<<<(unsigned)ctas, 2 * sg.var->threads, 2 * sg.var->smem, s>>>(a, ex);
+        CK(ctx, cudaGetLastError());
+        ctx->launches++;
+        return ADT_OK;
+    }
+    static const int smask_mode = getenv("ADT_FIR_SMASK") ? atoi(getenv("ADT_FIR_SMASK")) : 0;   // A/B: mask table in shared memory
+    if (smask_mode && sg.var->smask_real && sg.d.mask_is_real && !i16 && !shaped && !accum && !persistent && vt_mode != 2 && !tma_mode) {
+        sg.var->smask_real<<<grid, sg.var->threads, sg.var->smem + (size_t)sg.var->n * sizeof(float), s>>>(a, ex);
         CK(ctx, cudaGetLastError());
         ctx->launches++;
         return ADT_OK;

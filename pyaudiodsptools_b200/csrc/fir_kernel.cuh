@@ -119,6 +119,51 @@ __global__ void __launch_bounds__(C::T, MIN_CTAS) fir_block_kernel(const FirKern
     store_slice<C, IO, SHAPED, ACCUM>(v, t, it.ya, it.yb, it.m0, a.g, ex.shape);
 }
 
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+// MASK IN SHARED MEMORY (A/B, ADT_FIR_SMASK=1; real masks only): the l1tex hit rate of fir_block_kernel is 6 % —
+// the streaming windows push the 32 KB mask table out of L1, so the 32 mask loads per thread in the middle of
+// the DFT_32 -> mask -> IDFT_32 phase are L2 hits.  Here one thread hands the whole table to the bulk-copy (TMA)
+// engine at CTA start (cp.async.bulk.shared::cluster.global, completion on an mbarrier); it lands during stages
+// 1-2 and stage 3 reads it with conflict-free LDS.  Tile 67.6 KB + mask 32 KB = 99.6 KB -> still 2 CTAs/SM.
+template <class C, int MIN_CTAS>
+__global__ void __launch_bounds__(C::T, MIN_CTAS) fir_smask_kernel(const FirKernelArgs a, const FirExtra ex) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cf* tile = reinterpret_cast<cf*>(smem_raw);
+    float* smask = reinterpret_cast<float*>(smem_raw + (size_t)C::TILE * sizeof(cf));
+    __shared__ __align__(8) unsigned long long bar;
+    const int t = threadIdx.x;
+    const long long item = blockIdx.x;
+    const FirItem<float> it = fir_item<float>(a, item);
+    constexpr unsigned MASK_BYTES = C::N * sizeof(float);
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(MASK_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(smask)), "l"(a.mask), "r"(MASK_BYTES), "r"(smem_u32(&bar)) : "memory");
+    }
+    cf v[32];
+    load_window<C, IoF32>(v, t, it.xa, it.xb, it.ws, a.g.n_in);
+    fir_prefetch_l2<C::N, C::T, float>(a, item, t);
+    fwd_stage1<C>(v, t, a.tw1, tile);
+    __syncthreads();                 // also publishes the initialised mbarrier to every thread
+    fwd_stage2<C>(v, t, a.tw2, tile);
+    __syncwarp();
+    {
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done) : "r"(smem_u32(&bar)) : "memory");
+    }
+    mid_stage3<C, float>(v, t, smask, tile);
+    __syncwarp();
+    inv_stage2<C>(v, t, a.tw2, tile);
+    __syncthreads();
+    inv_stage1<C>(v, t, a.tw1, tile);
+    store_slice<C, IoF32, false>(v, t, it.ya, it.yb, it.m0, a.g, ex.shape);
+}
+
 // TWO VIRTUAL THREADS PER THREAD (A/B, ADT_FIR_VT=2): the CTA has T/2 threads and every phase runs twice, for
 // virtual thread ids t and t + T/2.  All exchanges are in place and separated by the same barriers, so the
 // result is identical; what changes is the schedule: 3 CTAs of 128 threads per SM instead of 2 of 256 (three
@@ -160,7 +205,6 @@ __global__ void __launch_bounds__(C::T / 2, MIN_CTAS) fir_vt2_kernel(const FirKe
 // instead of issuing 64 LDG.32.  Costs two extra block barriers (mbarrier init visible; all reads done before
 // stage 1 overwrites the tile) and keeps the same number of L1 wavefronts (64 LDS.32 replace 64 LDG.32).
 // Edge items (window crossing the ends of the row, odd last row, rows not 16-byte aligned) use the LDG path.
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 template <class C, class MaskT, int MIN_CTAS>
 __global__ void __launch_bounds__(C::T, MIN_CTAS) fir_tma_kernel(const FirKernelArgs a, const FirExtra ex) {

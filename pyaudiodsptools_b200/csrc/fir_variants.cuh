@@ -36,6 +36,7 @@ struct FirVariant {
     fir_kernel_fn tma_cplx, tma_real;          // TMA-fed window load (A/B, ADT_FIR_TMA=1) or null
     fir_kernel_fn vt2_cplx, vt2_real;          // two virtual threads per thread, T/2 threads per CTA (A/B, ADT_FIR_VT=2) or null
     fir_kernel_fn pp_cplx, pp_real;            // ping-pong schedule (fir_pingpong.cuh): 2 groups per CTA, persistent, or null
+    fir_kernel_fn smask_real;                  // real mask staged in shared memory by the bulk-copy engine (A/B, ADT_FIR_SMASK=1) or null
     fir_kernel_fn accum_cplx, accum_real;      // y += result: tap segments 1.. of a partitioned (long) filter, or null
     void (*build)(const float* mask, bool real_only, HostTables& out);
 };
@@ -67,6 +68,8 @@ FirVariant make_variant32(const char* name) {
     v.tma_cplx = v.tma_real = nullptr;
     v.vt2_cplx = v.vt2_real = nullptr;
     v.pp_cplx = v.pp_real = nullptr;
+    v.smask_real = nullptr;
+    if constexpr (TMA) v.smask_real = fir_smask_kernel<C, MIN_CTAS>;
 #ifdef ADT_FIR_PINGPONG_IMPL
     if constexpr (TMA && C::T == 256) {
         v.pp_cplx = fir_pingpong_kernel<C, cf>;
@@ -113,6 +116,7 @@ FirVariant make_variant16(const char* name) {
     v.tma_cplx = v.tma_real = nullptr;
     v.vt2_cplx = v.vt2_real = nullptr;
     v.pp_cplx = v.pp_real = nullptr;
+    v.smask_real = nullptr;
     v.accum_cplx = v.accum_real = nullptr;
     v.build = [](const float* mask, bool real_only, HostTables& out) {
         out.tw1 = build16_tw1<C>();
